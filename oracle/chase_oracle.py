@@ -1,0 +1,638 @@
+"""TEST INFRASTRUCTURE — CPU restatement of the reference algorithm (numpy/scipy).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` leg of
+``bench.py`` may import this module; the product path never does.
+
+It restates, in plain numpy, the Hermitian ChASE solve of the reference:
+
+* driver      /root/reference/algorithm/algorithm.inc:1376-1788 (``solve``),
+              :942-1009 (``filter``), :136-193 (``calc_degrees``),
+              :519-578 (``locking``), :1067-1214 (``lanczos`` + DoS)
+* backend     /root/reference/Impl/chase_cpu/chase_cpu.hpp:291-851 (ChASECPU)
+* kernels     /root/reference/linalg/internal/cpu/cholqr1.hpp:49-196,
+              lanczos.hpp:45-209, rayleighRitz.hpp:60-120, residuals.hpp:45-80
+
+Third-party arithmetic the reference delegates to BLAS/LAPACK (gemm, herk,
+potrf, trsm, heevd, stemr; vendor unpinned by the reference, OpenBLAS 0.3.15 in
+``oracle/_ref``) is done here with numpy/scipy (whatever BLAS they bundle).
+
+Pinned: ``tests/test_oracle_vs_reference.py`` checks this restatement against
+the golden call traces of the unmodified reference CPU solver
+(``tests/golden/*.json``, produced by ``oracle/_ref/chase_ref_cpu_*`` through
+``tests/golden/make_golden.py``): identical iteration count, filtered-vector
+count, HEMM schedule, QR variants and lock counts; eigenvalues to 1e-10.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.linalg as sla
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# --------------------------------------------------------------------------
+# libstdc++ mt19937 + normal_distribution stream (chase_cpu.hpp:296-309)
+# --------------------------------------------------------------------------
+def _mtlib():
+    path = os.path.join(_HERE, "_build", "libmtnormal.so")
+    if not os.path.exists(path):
+        import subprocess
+
+        subprocess.check_call(["make", "-C", _HERE, "helpers"], stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(path)
+    lib.mt_normal_fill_skip.argtypes = [ctypes.c_uint, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
+    return lib
+
+
+def mt_normal(seed: int, n: int, skip: int = 0) -> np.ndarray:
+    out = np.empty(n, dtype=np.float64)
+    _mtlib().mt_normal_fill_skip(seed, skip, n, out.ctypes.data)
+    return out
+
+
+def init_vectors(N: int, ncols: int, dtype, seed: int = 1337) -> np.ndarray:
+    """Column-major N x ncols start block exactly as ChASECPU::initVecs fills it."""
+    dtype = np.dtype(dtype)
+    if dtype.kind == "c":
+        s = mt_normal(seed, 2 * N * ncols)
+        # getRandomT<complex>(f) = complex(f(), f()); g++ evaluates the two
+        # calls right-to-left, so the FIRST draw lands in the imaginary part
+        # (verified against chase_ref_cpu_z --initvecs-only in the tests).
+        v = (s[1::2] + 1j * s[0::2]).astype(dtype)
+    else:
+        v = mt_normal(seed, N * ncols).astype(dtype)
+    return np.asfortranarray(v.reshape(ncols, N).T)
+
+
+# --------------------------------------------------------------------------
+# matrices (tests/noinput.cpp:67-74; examples/2_input_output.cpp:250-262)
+# --------------------------------------------------------------------------
+def clement(N: int, dtype=np.float64) -> np.ndarray:
+    H = np.zeros((N, N), dtype=dtype, order="F")
+    i = np.arange(N - 1)
+    v = np.sqrt((i * (N + 1 - i)).astype(np.float64))
+    H[i + 1, i] = v
+    H[i, i + 1] = v
+    return H
+
+
+def uniform_spectrum(N: int, dmax: float = 100.0, eps: float = 1e-4) -> np.ndarray:
+    k = np.arange(N, dtype=np.float64)
+    return dmax * (eps + k * (1.0 - eps) / float(N))
+
+
+def uniform_diag(N: int, dtype=np.float64) -> np.ndarray:
+    H = np.zeros((N, N), dtype=dtype, order="F")
+    H[np.arange(N), np.arange(N)] = uniform_spectrum(N)
+    return H
+
+
+def dense_from_spectrum(lam: np.ndarray, dtype=np.float64, seed: int = 7, nrefl: int = 3) -> np.ndarray:
+    """A = Q diag(lam) Q^H with Q a product of `nrefl` Householder reflectors."""
+    N = lam.shape[0]
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(seed)
+    A = np.zeros((N, N), dtype=dtype, order="F")
+    A[np.arange(N), np.arange(N)] = lam
+    for _ in range(nrefl):
+        v = rng.standard_normal(N)
+        if dtype.kind == "c":
+            v = v + 1j * rng.standard_normal(N)
+        v = (v / np.linalg.norm(v)).astype(dtype)
+        w = A @ v
+        s = np.vdot(v, w)
+        A -= 2 * np.outer(v, w.conj())
+        A -= 2 * np.outer(w, v.conj())
+        A += 4 * s * np.outer(v, v.conj())
+    A = 0.5 * (A + A.conj().T)
+    return np.asfortranarray(A)
+
+
+def perturb_hermitian(H: np.ndarray, stream: np.ndarray, perturb: float) -> int:
+    """In-place element-wise perturbation of oracle/ref_driver.cpp (mirrors
+    tests/noinput.cpp:120-134); returns the number of stream values consumed."""
+    N = H.shape[0]
+    cplx = np.iscomplexobj(H)
+    pos = 0
+    for i in range(1, N):
+        cnt = i - 1
+        if cnt <= 0:
+            continue
+        if cplx:
+            blk = stream[pos:pos + 2 * cnt]
+            e = (blk[0::2] + 1j * blk[1::2]) * perturb
+            pos += 2 * cnt
+        else:
+            e = stream[pos:pos + cnt] * perturb
+            pos += cnt
+        H[1:i, i] += e
+        H[i, 1:i] += np.conj(e)
+    return pos
+
+
+# --------------------------------------------------------------------------
+# kernels (linalg/internal/cpu)
+# --------------------------------------------------------------------------
+def _eps(dtype):
+    return np.finfo(np.dtype(dtype).char.lower() if np.dtype(dtype).kind == "c" else dtype).eps
+
+
+def _real_dtype(dtype):
+    return np.zeros(1, dtype=dtype).real.dtype
+
+
+def _chol_step(V: np.ndarray, shift: float = 0.0) -> int:
+    """one round: G = V^H V (+shift I), R = chol(G) upper, V <- V R^-1. cholqr1.hpp:49-80"""
+    G = V.conj().T @ V
+    if shift:
+        G[np.diag_indices_from(G)] += shift
+    try:
+        Rm = sla.cholesky(G, lower=False, check_finite=False)
+    except sla.LinAlgError:
+        return 1
+    V[...] = sla.solve_triangular(Rm, V.conj().T, trans="C", lower=False, check_finite=False).conj().T
+    return 0
+
+
+def cholqr1(V):
+    return _chol_step(V)
+
+
+def cholqr2(V):
+    info = _chol_step(V)
+    if info:
+        return info
+    return _chol_step(V)
+
+
+def shifted_cholqr2(V):
+    """cholqr1.hpp:136-196: shift = sqrt(m) * sum|G_ii| * eps (double), 10 * sum|G_ii| * eps (float)."""
+    m = V.shape[0]
+    G = V.conj().T @ V
+    nrmf = float(np.sum(np.abs(np.diag(G))))
+    rd = _real_dtype(V.dtype)
+    if rd == np.float32:
+        shift = 10.0 * nrmf * float(np.finfo(np.float32).eps)
+    else:
+        shift = math.sqrt(float(m)) * nrmf * float(np.finfo(np.float64).eps)
+    info = _chol_step(V, shift)
+    if info:
+        return info
+    _chol_step(V)
+    return _chol_step(V)
+
+
+def householder_qr(V):
+    Q, _ = np.linalg.qr(V)
+    V[...] = Q
+
+
+@dataclass
+class Trace:
+    calls: list = field(default_factory=list)
+    swaps: int = 0
+    hemm_calls: int = 0
+    filtered_vecs: int = 0
+    iterations: int = 0
+
+    def add(self, s):
+        self.calls.append(s)
+
+
+class OracleBackend:
+    """numpy mirror of ChASECPU (chase_cpu.hpp), Hermitian case only."""
+
+    def __init__(self, H: np.ndarray, nev: int, nex: int, V0: np.ndarray | None = None):
+        self.H = H  # never modified: Shift is tracked in self.shift and applied as A - cI
+        self.N = H.shape[0]
+        self.nev, self.nex, self.nevex = nev, nex, nev + nex
+        self.dtype = H.dtype
+        self.rdtype = _real_dtype(H.dtype)
+        self.V1 = np.zeros((self.N, self.nevex), dtype=self.dtype, order="F") if V0 is None else np.asfortranarray(V0.copy())
+        self.V2 = np.zeros_like(self.V1)
+        self.ritzv = np.zeros(self.nevex, dtype=self.rdtype)
+        self.resid = np.zeros(self.nevex, dtype=self.rdtype)
+        self.locked = 0
+        self.trace = Trace()
+        self.qr_variants = []
+
+    # -- ChaseBase virtuals --------------------------------------------------
+    def Start(self):
+        self.locked = 0
+
+    def initVecs(self, random: bool):
+        if random:
+            self.V1 = init_vectors(self.N, self.nevex, self.dtype)
+        self.V2[...] = self.V1
+
+    def Shift(self, c, isunshift=False):
+        # chase_cpu.hpp:392-397 adds c to the diagonal of H itself.
+        self.H[np.arange(self.N), np.arange(self.N)] += self.dtype.type(c)
+
+    def HEMM(self, block, alpha, beta, offset_left, offset_right=0):
+        ncols = block - offset_right if offset_right < block else 0
+        self.trace.hemm_calls += 1
+        self.trace.filtered_vecs += ncols
+        if ncols:
+            s = slice(offset_left + self.locked, offset_left + self.locked + ncols)
+            a = self.dtype.type(alpha)
+            b = self.dtype.type(beta)
+            self.V2[:, s] = a * (self.H @ self.V1[:, s]) + b * self.V2[:, s]
+        self.V1, self.V2 = self.V2, self.V1
+
+    def QR(self, fixednev, cond):
+        # chase_cpu.hpp:597-781
+        self.V2[:, : self.locked] = self.V1[:, : self.locked]
+        dbl = self.rdtype == np.float64
+        upper = 1e8 if dbl else 1e4
+        lower = 2e1 if dbl else 1e1
+        Vw = self.V1
+        work = Vw
+        if not dbl:
+            # QR_DOUBLE_PRECISION only affects the Householder fallback on the CPU backend
+            pass
+        if cond > upper:
+            info = shifted_cholqr2(work)
+            self.qr_variants.append("shifted2")
+        elif cond < lower:
+            info = cholqr1(work)
+            self.qr_variants.append("chol1")
+        else:
+            info = cholqr2(work)
+            self.qr_variants.append("chol2")
+        if info != 0:
+            householder_qr(work)
+            self.qr_variants[-1] += "+householder"
+        self.V1[:, : self.locked] = self.V2[:, : self.locked]
+
+    def RR(self, block):
+        # rayleighRitz.hpp:60-120 : W = A^H Q ; G = W^H Q ; heevd(lower) ; V2 = Q Z ; swap
+        s = slice(self.locked, self.locked + block)
+        Q = self.V1[:, s]
+        W = self.H.conj().T @ Q
+        G = W.conj().T @ Q
+        w, Z = sla.eigh(G, lower=True, driver="evd", check_finite=False)
+        self.ritzv[s] = w.astype(self.rdtype)
+        self.V2[:, s] = Q @ Z.astype(self.dtype)
+        self.V1, self.V2 = self.V2, self.V1
+
+    def Resd(self):
+        # residuals.hpp:45-80 on the nevex-locked trailing columns
+        s = slice(self.locked, self.nevex)
+        V = self.V1[:, s]
+        W = self.H @ V - V * self.ritzv[s].astype(self.dtype)
+        self.V2[:, s] = W
+        self.resid[s] = np.linalg.norm(W, axis=0).astype(self.rdtype)
+
+    def Swap(self, i, j):
+        self.trace.swaps += 1
+        self.V1[:, [i, j]] = self.V1[:, [j, i]]
+
+    def Lock(self, n):
+        self.locked += n
+
+    def Lanczos(self, M, numvec):
+        """lanczos.hpp:45-209 (multi-vector). Returns upperb, Theta, Tau, ritzV(last run)."""
+        N = self.N
+        dt = self.dtype
+        v1 = np.array(self.V1[:, :numvec], order="F", copy=True)
+        v0 = np.zeros_like(v1)
+        d = np.zeros((M, numvec), dtype=self.rdtype)
+        e = np.zeros((M, numvec), dtype=self.rdtype)
+        v1 /= np.linalg.norm(v1, axis=0).astype(self.rdtype)
+        r_beta = np.zeros(numvec, dtype=self.rdtype)
+        AH = self.H.conj().T
+        for k in range(M):
+            self.V1[:, k] = v1[:, numvec - 1]
+            v2 = AH @ v1
+            alpha = np.einsum("ij,ij->j", v1.conj(), v2)
+            v2 -= v1 * alpha
+            d[k, :] = alpha.real
+            if k > 0:
+                v2 -= v0 * r_beta.astype(dt)
+            r_beta = np.linalg.norm(v2, axis=0).astype(self.rdtype)
+            if k == M - 1:
+                break
+            v2 *= (1.0 / r_beta).astype(dt)
+            e[k, :] = r_beta
+            v0, v1 = v1, v2
+        self.V1[:, :numvec] = v1
+        Theta = np.zeros((numvec, M), dtype=self.rdtype)
+        Tau = np.zeros((numvec, M), dtype=self.rdtype)
+        ritzV = None
+        for i in range(numvec):
+            w, Z = sla.eigh_tridiagonal(d[:, i].astype(np.float64), e[: M - 1, i].astype(np.float64), lapack_driver="stemr")
+            Theta[i, :] = w
+            Tau[i, :] = np.abs(Z[0, :]) ** 2
+            ritzV = Z
+        upperb = max(max(abs(Theta[i, 0]), abs(Theta[i, M - 1])) + abs(r_beta[i]) for i in range(numvec))
+        return self.rdtype.type(upperb), Theta, Tau, ritzV
+
+    def LanczosDos(self, idx, m, ritzV):
+        # chase_cpu.hpp:376-390
+        self.V2[:, :idx] = self.V1[:, :m] @ ritzV[:, :idx].astype(self.dtype)
+        self.V1[:, :m] = self.V2[:, :m]
+
+
+# --------------------------------------------------------------------------
+# driver (algorithm.inc)
+# --------------------------------------------------------------------------
+@dataclass
+class Config:
+    tol: float = 1e-10
+    deg: int = 20
+    max_deg: int = 36
+    deg_extra: int = 2
+    max_iter: int = 25
+    lanczos_iter: int = 25
+    num_lanczos: int = 4
+    opt: bool = True
+    approx: bool = False
+    decaying_rate: float = 1.0
+
+    @staticmethod
+    def for_dtype(dtype):
+        if _real_dtype(dtype) == np.float32:
+            return Config(tol=1e-5, deg=10, max_deg=18, lanczos_iter=12)
+        return Config()
+
+
+def _lanczos_dos(be: OracleBackend, cfg: Config, lanczos_iter: int, random: bool):
+    """algorithm.inc:1067-1214; returns upperb and fills be.ritzv when random."""
+    N, nevex = be.N, be.nevex
+    numvec, m = cfg.num_lanczos, lanczos_iter
+    rd = be.rdtype
+    if not random:
+        raise NotImplementedError  # handled by caller
+    upperb, Theta, Tau, ritzV = be.Lanczos(m, numvec)
+    be.trace.add(f"Lanczos {m} {numvec} {float(upperb)!r}")
+    Th = Theta.reshape(-1).astype(np.float64)
+    Ta = Tau.reshape(-1).astype(np.float64)
+    ThS = np.sort(Th)
+    lam = rd.type(ThS[0])
+    sigma = 0.25
+    threshold = 2 * sigma * sigma / 10
+    search = float(nevex) / float(N)
+    lowerb = rd.type(0)
+    prev = 0.0
+    n = numvec * m
+    for i in range(n - 1):
+        x = ThS[i]
+        curr = 0.0
+        for j in range(n):
+            if x < Th[j] - threshold:
+                pass
+            elif x > Th[j] + threshold:
+                curr += Ta[j]
+            else:
+                curr += Ta[j] * 0.5 * (1 + math.erf((x - Th[j]) / math.sqrt(2 * sigma * sigma)))
+        curr /= numvec
+        if curr > search:
+            if abs(curr - search) < abs(prev - search):
+                lowerb = rd.type(ThS[i + 1] if i + 1 < n else ThS[i])
+            else:
+                lowerb = rd.type(ThS[i])
+            break
+        prev = curr
+    idx = 0
+    last = Theta[numvec - 1]
+    for i in range(m):
+        if last[i] > lowerb:
+            idx = i - 1
+            break
+    if idx > 0:
+        be.trace.add(f"LanczosDos {idx} {m}")
+        be.LanczosDos(idx, m, ritzV)
+    rv = be.ritzv
+    for i in range(max(idx, 0)):
+        rv[i] = last[i]
+    for i in range(max(idx, 0), nevex - 1):
+        rv[i] = lam
+    rv[nevex - 1] = lowerb
+    for i in range(1, idx):
+        j = i * (nevex // idx)
+        be.Swap(i, j)
+        rv[i], rv[j] = rv[j], rv[i]
+    return upperb
+
+
+def _lanczos_single(be: OracleBackend, m: int):
+    """lanczos.hpp:231-330 single-vector variant (approx mode): upper bound only."""
+    dt = be.dtype
+    rd = be.rdtype
+    v1 = be.V1[:, 0].copy()
+    v1 /= rd.type(np.linalg.norm(v1))
+    v0 = np.zeros_like(v1)
+    d = np.zeros(m, dtype=rd)
+    e = np.zeros(m, dtype=rd)
+    AH = be.H.conj().T
+    r_beta = rd.type(0)
+    for k in range(m):
+        v2 = AH @ v1
+        alpha = np.vdot(v1, v2)
+        v2 -= alpha * v1
+        d[k] = alpha.real
+        if k > 0:
+            v2 -= dt.type(r_beta) * v0
+        r_beta = rd.type(np.linalg.norm(v2))
+        if k == m - 1:
+            break
+        v2 *= dt.type(1.0 / r_beta)
+        e[k] = r_beta
+        v0, v1 = v1, v2
+    w = sla.eigh_tridiagonal(d.astype(np.float64), e[: m - 1].astype(np.float64), eigvals_only=True, lapack_driver="stemr")
+    return rd.type(max(abs(w[0]), abs(w[-1])) + abs(r_beta))
+
+
+def _calc_degrees(be, cfg, unconverged, nex, upperb, lowerb, tol, ritzv, resid, degrees, locked):
+    rd = be.rdtype
+    c = (upperb + lowerb) / rd.type(2)
+    e = (upperb - lowerb) / rd.type(2)
+    for i in range(unconverged - nex):
+        t = (ritzv[i] - c) / e
+        sq = np.sqrt(np.abs(t * t - 1))
+        rho = max(abs(t - sq), abs(t + sq))
+        dg = int(math.ceil(abs(math.log(float(resid[i]) / tol) / math.log(float(rho)))))
+        if rd == np.float32:
+            dg = max(dg, 8)
+        degrees[i] = min(dg + cfg.deg_extra, cfg.max_deg)
+    for i in range(unconverged - nex, unconverged):
+        degrees[i] = degrees[unconverged - 1 - nex]
+    for i in range(unconverged):
+        degrees[i] += degrees[i] % 2
+    for j in range(unconverged - 1):
+        for k in range(j, unconverged):
+            if degrees[k] < degrees[j]:
+                degrees[k], degrees[j] = degrees[j], degrees[k]
+                ritzv[k], ritzv[j] = ritzv[j], ritzv[k]
+                resid[k], resid[j] = resid[j], resid[k]
+                be.Swap(k + locked, j + locked)
+    return int(degrees[unconverged - 1])
+
+
+def _filter(be, unprocessed, deg, degrees, lambda_1, lower, upper):
+    rd = be.rdtype
+    c = (upper + lower) / rd.type(2)
+    e = (upper - lower) / rd.type(2)
+    sigma_1 = e / (lambda_1 - c)
+    sigma = sigma_1
+    be.trace.add(f"Shift {float(-c)!r} 0")
+    be.Shift(-c)
+    alpha = sigma_1 / e
+    off = 0
+    num_mult = 0
+    dpos = 0
+    be.trace.add(f"HEMM {unprocessed} {off}")
+    be.HEMM(unprocessed, alpha, 0.0, off)
+    num_mult += 1
+    while unprocessed >= 0 and degrees[dpos] <= num_mult:
+        dpos += 1
+        unprocessed -= 1
+        off += 1
+    for _ in range(2, deg + 1):
+        sigma_new = rd.type(1.0) / (rd.type(2.0) / sigma_1 - sigma)
+        alpha = rd.type(2.0) * sigma_new / e
+        beta = -sigma * sigma_new
+        be.trace.add(f"HEMM {unprocessed} {off}")
+        be.HEMM(unprocessed, alpha, beta, off)
+        sigma = sigma_new
+        num_mult += 1
+        while unprocessed != 0 and degrees[dpos] <= num_mult:
+            dpos += 1
+            unprocessed -= 1
+            off += 1
+    be.Shift(+c, True)
+
+
+def _locking(be, unconverged, tol, ritzv, resid, residLast, locked):
+    index = sorted(range(unconverged), key=lambda a: ritzv[a])  # std::sort on distinct keys
+    converged = 0
+    early = 0
+    for k in range(unconverged):
+        j = index[k]
+        if resid[j] <= tol or (resid[j] >= residLast[j] and resid[j] < 100.0 * tol):
+            if resid[j] > tol:
+                early += 1
+            if j != converged:
+                resid[j], resid[converged] = resid[converged], resid[j]
+                residLast[j], residLast[converged] = residLast[converged], residLast[j]
+                ritzv[j], ritzv[converged] = ritzv[converged], ritzv[j]
+                be.Swap(j + locked, converged + locked)
+            converged += 1
+    return converged, early
+
+
+def solve(be: OracleBackend, cfg: Config) -> Trace:
+    """algorithm.inc:1376-1788 (Hermitian branch)."""
+    rd = be.rdtype
+    N, nev, nex, nevex = be.N, be.nev, be.nex, be.nevex
+    tr = be.trace
+    be.Start()
+    unconverged = nevex
+    fmax = np.finfo(rd).max
+    residLast_ = np.full(nevex, fmax, dtype=rd)
+    be.resid[:] = fmax
+    deg = cfg.deg + cfg.deg % 2
+    deg = min(deg, cfg.max_deg)
+    degrees_ = [deg] * nevex
+    random = not cfg.approx
+    be.initVecs(random)
+    if random:
+        tr.add("QR 0 1")
+        be.QR(0, 1.0)
+    lanczos_iter = min(nevex, min(N // 2, cfg.lanczos_iter))
+    if 2 * (lanczos_iter // 2) < lanczos_iter:
+        lanczos_iter -= 1
+        cfg.lanczos_iter = lanczos_iter
+    if random:
+        upperb = _lanczos_dos(be, cfg, lanczos_iter, True)
+    else:
+        upperb = _lanczos_single(be, lanczos_iter)
+    locked = 0
+    iteration = 0
+    ritzv_all, resid_all = be.ritzv, be.resid
+    lowerb = rd.type(np.max(ritzv_all[:unconverged])) * rd.type(cfg.decaying_rate)
+    lam = rd.type(np.min(ritzv_all[:nevex]))
+    tol = cfg.tol
+    while unconverged > nex and iteration < cfg.max_iter:
+        ritzv = ritzv_all[locked:]
+        resid = resid_all[locked:]
+        residLast = residLast_[locked:]
+        degrees = degrees_[locked:]
+        if np.all(resid[:unconverged] <= 0.5):
+            lowerb = ritzv[unconverged - 1]
+        if lowerb > upperb:
+            lowerb = upperb
+        residLast[:unconverged] = np.minimum(residLast[:unconverged], resid[:unconverged])
+        if cfg.opt and iteration != 0:
+            deg = _calc_degrees(be, cfg, unconverged, nex, upperb, lowerb, tol, ritzv, resid, degrees, locked)
+            degrees_[locked:] = degrees
+        tr.add(f"iter {iteration} lambda {float(lam)!r} lowerb {float(lowerb)!r} upperb {float(upperb)!r} unconv {unconverged}")
+        _filter(be, unconverged, deg, degrees, lam, lowerb, upperb)
+        cc = (upperb + lowerb) / rd.type(2)
+        ee = (upperb - lowerb) / rd.type(2)
+        t_1 = (ritzv_all[0] - cc) / ee
+        t_k = (ritzv[0] - cc) / ee
+        with np.errstate(invalid="ignore"):
+            rho_1 = max(abs(t_1 - np.sqrt(t_1 * t_1 - 1)), abs(t_1 + np.sqrt(t_1 * t_1 - 1)))
+            rho_k = max(abs(t_k - np.sqrt(t_k * t_k - 1)), abs(t_k + np.sqrt(t_k * t_k - 1)))
+        dmax = max(degrees[: nevex - locked])
+        cond = rd.type(float(rho_k) ** degrees[0] * float(rho_1) ** (dmax - degrees[0]))
+        tr.add(f"QR {locked} {float(cond)!r}")
+        be.QR(locked, cond)
+        be.RR(unconverged)
+        tr.add(f"RR {unconverged}")
+        be.Resd()
+        new_converged, _ = _locking(be, unconverged - nex, tol, ritzv, resid, residLast, locked)
+        tr.add(f"Lock {new_converged}")
+        be.Lock(new_converged)
+        locked += new_converged
+        unconverged -= new_converged
+        iteration += 1
+    # final sort of the first nev pairs (algorithm.inc:1726-1774)
+    perm = sorted(range(nev), key=lambda i: ritzv_all[i])
+    visited = [False] * nev
+    for i in range(nev):
+        if visited[i] or perm[i] == i:
+            continue
+        cyc = []
+        cur = i
+        while not visited[cur]:
+            visited[cur] = True
+            cyc.append(cur)
+            cur = perm[cur]
+        t_r, t_s = ritzv_all[i], resid_all[i]
+        for k in range(len(cyc) - 1):
+            ritzv_all[cyc[k]] = ritzv_all[cyc[k + 1]]
+            resid_all[cyc[k]] = resid_all[cyc[k + 1]]
+        ritzv_all[cyc[-1]] = t_r
+        resid_all[cyc[-1]] = t_s
+        for k in range(len(cyc) - 1):
+            be.Swap(cyc[k], cyc[k + 1])
+    tr.iterations = iteration
+    return tr
+
+
+def solve_problem(H: np.ndarray, nev: int, nex: int, cfg: Config | None = None, V0: np.ndarray | None = None):
+    """Convenience wrapper: returns (ritzv, resid, V, trace, backend). H is not modified."""
+    H = np.asfortranarray(H.copy())
+    cfg = cfg or Config.for_dtype(H.dtype)
+    be = OracleBackend(H, nev, nex, V0)
+    tr = solve(be, cfg)
+    return be.ritzv.copy(), be.resid.copy(), be.V1.copy(), tr, be
+
+
+# Stand-alone single-kernel oracles used by the kernel-level parity tests ----
+def gemm_filter_step(A, B, C, alpha, beta, shift):
+    """C <- alpha*(A - shift*I) B + beta*C  (one filter step, algorithm.inc:985-990)."""
+    return alpha * (A @ B - shift * B) + beta * C
+
+
+def residual_norms(A, V, theta):
+    """residuals.hpp:45-80."""
+    return np.linalg.norm(A @ V - V * theta, axis=0)

@@ -1,0 +1,61 @@
+"""Regenerates tests/golden/*.json by running the UNMODIFIED reference CPU solver
+(oracle/_ref/chase_ref_cpu_<type>, built from /root/reference by oracle/Makefile).
+
+Run in the build container only (needs /root/reference to build oracle/_ref):
+    make -C oracle all && python tests/golden/make_golden.py
+
+Each fixture records, for one problem (or a short sequence), the reference's
+iteration count, filtered-vector count, final Ritz values / residuals and the
+full ChaseBase call trace (HEMM schedule, QR condition estimates, Ritz values
+and residuals per iteration, lock counts).
+"""
+import json
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+CASES = {
+    # BASELINE.json configs[0]: Clement N=1001, nev=100, nex=40, real double
+    "c1_clement_d_N1001": dict(type="d", N=1001, nev=100, nex=40, matrix="clement", tol=1e-10, deg=20),
+    "c1_clement_z_N1001": dict(type="z", N=1001, nev=100, nex=40, matrix="clement", tol=1e-10, deg=20),
+    # /root/reference/tests/chase_serial_solve.cpp sizes (N=256, nev=24, nex=16, deg 16)
+    "serial_clement_d_N256": dict(type="d", N=256, nev=24, nex=16, matrix="clement", tol=1e-10, deg=16),
+    "serial_clement_z_N256": dict(type="z", N=256, nev=24, nex=16, matrix="clement", tol=1e-10, deg=16),
+    "serial_clement_s_N256": dict(type="s", N=256, nev=24, nex=16, matrix="clement", tol=1e-5, deg=16),
+    "serial_clement_c_N256": dict(type="c", N=256, nev=24, nex=16, matrix="clement", tol=1e-5, deg=16),
+    # scaled BASELINE.json configs[1]: uniform spectrum (reference --isMatGen generator)
+    "c2s_uniform_d_N2000": dict(type="d", N=2000, nev=100, nex=40, matrix="uniform", tol=1e-10, deg=20),
+    # tests/noinput.cpp-style correlated sequence (approximate start vectors)
+    "seq_clement_z_N400": dict(type="z", N=400, nev=40, nex=20, matrix="clement", tol=1e-10, deg=20, seq=3, perturb=1e-4),
+    "seq_clement_d_N400": dict(type="d", N=400, nev=40, nex=20, matrix="clement", tol=1e-10, deg=20, seq=3, perturb=1e-4),
+    # no degree optimisation
+    "noopt_clement_d_N300": dict(type="d", N=300, nev=30, nex=10, matrix="clement", tol=1e-10, deg=20, opt=0),
+}
+
+
+def run_case(name, c):
+    exe = os.path.join(ROOT, "oracle", "_ref", f"chase_ref_cpu_{c['type']}")
+    out = os.path.join(HERE, name + ".json")
+    cmd = [exe, "--out", out]
+    for k, v in c.items():
+        if k == "type":
+            continue
+        cmd += [f"--{k}", str(v)]
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="8", OMP_NUM_THREADS="8")
+    subprocess.check_call(cmd, env=env, stdout=subprocess.DEVNULL)
+    j = json.load(open(out))
+    # keep fixtures small: round-trip through json with no extra whitespace
+    json.dump(j, open(out, "w"), separators=(",", ":"))
+    p = j["problems"]
+    print(name, [(q["iterations"], q["filtered_vecs"]) for q in p], os.path.getsize(out) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    for n, c in CASES.items():
+        if only and n not in only:
+            continue
+        run_case(n, c)

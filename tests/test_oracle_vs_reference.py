@@ -1,0 +1,67 @@
+"""Pins oracle/chase_oracle.py (numpy restatement) against the golden traces of the
+UNMODIFIED reference CPU solver (tests/golden/*.json, see make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import chase_oracle as co
+from tests.golden_util import DT, load, parse_trace
+
+
+def _matrix(g):
+    dt = DT[g["type"]]
+    if g["matrix"] == "clement":
+        return co.clement(g["N"], dt)
+    if g["matrix"] == "uniform":
+        return co.uniform_diag(g["N"], dt)
+    raise ValueError(g["matrix"])
+
+
+def _oracle_trace(tr):
+    hemm = [tuple(int(x) for x in c.split()[1:3]) for c in tr.calls if c.startswith("HEMM")]
+    qr = [(int(c.split()[1]), float(c.split()[2])) for c in tr.calls if c.startswith("QR")]
+    locks = [int(c.split()[1]) for c in tr.calls if c.startswith("Lock")]
+    return hemm, qr, locks
+
+
+@pytest.mark.parametrize(
+    "name",
+    ["c1_clement_d_N1001", "serial_clement_d_N256", "serial_clement_z_N256", "c2s_uniform_d_N2000", "noopt_clement_d_N300"],
+)
+def test_oracle_matches_reference_trace(name):
+    g = load(name)
+    p = g["problems"][0]
+    ref = parse_trace(p["trace"])
+    cfg = co.Config.for_dtype(DT[g["type"]])
+    cfg.tol, cfg.deg, cfg.opt = g["tol"], g["deg"], bool(g["opt"])
+    rv, rs, V, tr, be = co.solve_problem(_matrix(g), g["nev"], g["nex"], cfg)
+    hemm, qr, locks = _oracle_trace(tr)
+    assert tr.iterations == p["iterations"]
+    assert tr.filtered_vecs == p["filtered_vecs"]
+    assert hemm == [(b, o) for (b, o, _, _) in ref["hemm"]]  # identical degree schedule
+    assert locks == ref["locks"]
+    assert [q[0] for q in qr] == [q[0] for q in ref["qr"]]
+    for (_, c1), (_, c2) in zip(qr, ref["qr"]):
+        assert c1 == pytest.approx(c2, rel=1e-6)
+    nev = g["nev"]
+    refv = np.array(p["ritzv"][:nev])
+    # north_star tolerance: eigenvalues within 1e-10 relative in FP64
+    assert np.max(np.abs(rv[:nev] - refv) / np.abs(refv)) < 1e-10
+    assert np.all(rs[:nev] <= g["tol"] * 100)  # early locking allows < 100 tol (algorithm.inc:543-544)
+    assert tr.swaps == p["swaps"]
+
+
+def test_clement_known_answer():
+    """Known-answer: lowest Clement eigenvalues are -N, -N+2, ... (tests/noinput.cpp matrix)."""
+    g = load("c1_clement_d_N1001")
+    rv = np.array(g["problems"][0]["ritzv"][:100])
+    assert np.allclose(rv, -1001 + 2 * np.arange(100), atol=1e-9)
+
+
+def test_start_vectors_match_libstdcxx_stream():
+    v = co.init_vectors(8, 3, np.float64)
+    s = co.mt_normal(1337, 24)
+    assert np.array_equal(v.T.reshape(-1), s)
+    z = co.init_vectors(8, 3, np.complex128)
+    s = co.mt_normal(1337, 48)
+    assert np.array_equal(z.T.reshape(-1).imag, s[0::2])
+    assert np.array_equal(z.T.reshape(-1).real, s[1::2])
