@@ -1,0 +1,277 @@
+// chase_b200 — HBM-bound helper kernels: copies, column permutation (batched
+// Swap), column norms (residuals), the Lanczos A^H*[v1..v4] product and its
+// fused vector updates, start-vector RNG, Hermitian check.
+//
+// Reference counterparts: /root/reference/linalg/internal/cuda/lacpy.cu:62-496,
+// residuals.cu:113-296, lanczos_kernels.cu:40-1188 (one 256-thread block per
+// Lanczos vector), random_normal_distribution.cu:21-93, shiftDiagonal.cu:23-50.
+#pragma once
+#include "common.cuh"
+
+namespace cb2
+{
+
+template <class T>
+__global__ void lacpy_kernel(long long rows, long long cols, const T* src, long long lds, T* dst, long long ldd)
+{
+    const long long j = blockIdx.y;
+    for (long long jj = j; jj < cols; jj += gridDim.y)
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+             i += (long long)gridDim.x * blockDim.x)
+            dst[i + jj * ldd] = src[i + jj * lds];
+}
+
+// dst[:, dcols[t]] = src[:, scols[t]] for t < cnt  (src and dst must not alias)
+template <class T>
+__global__ void gather_cols_kernel(long long rows, int cnt, const int* scols, const int* dcols, const T* src,
+                                   long long lds, T* dst, long long ldd)
+{
+    for (int t = blockIdx.y; t < cnt; t += gridDim.y)
+    {
+        const long long s = scols[t], d = dcols[t];
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+             i += (long long)gridDim.x * blockDim.x)
+            dst[i + d * ldd] = src[i + s * lds];
+    }
+}
+
+// out[j] = ||X[:, j]||_2 (take_sqrt) or its square
+template <class T>
+__global__ void __launch_bounds__(256) colnorm_kernel(long long rows, const T* X, long long ldx, double* out,
+                                                       int take_sqrt)
+{
+    __shared__ double sh[32];
+    const long long j = blockIdx.x;
+    const T* x = X + j * ldx;
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+        acc += cabs2(widen(x[i]));
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0)
+        out[j] = take_sqrt ? sqrt(acc) : acc;
+}
+
+// X[:, j] *= 1/||X[:, j]||
+template <class T>
+__global__ void __launch_bounds__(1024) normalize_cols_kernel(long long rows, T* X, long long ldx)
+{
+    using C = typename Traits<T>::comp;
+    __shared__ double sh[32];
+    T* x = X + (long long)blockIdx.x * ldx;
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+        acc += cabs2(widen(x[i]));
+    acc = block_sum(acc, sh);
+    // the reference rounds the norm and its reciprocal to Base<T> (cpu/lanczos.hpp:69-82)
+    using R = typename Traits<T>::real;
+    const R nrm = (R)sqrt(acc);
+    const double inv = (double)(R)(1 / nrm);
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+        x[i] = narrow<T>(cmul(inv, (C)widen(x[i])));
+}
+
+// Y[j, v] = sum_i conj(A[i, j]) * X[i, v]   (one warp per column j of A)
+template <class T, int NV>
+__global__ void __launch_bounds__(256) gemv_conjT_kernel(long long rows, long long cols, const T* A, long long lda,
+                                                          const T* X, long long ldx, T* Y, long long ldy)
+{
+    using C = typename Traits<T>::comp;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long j = warp; j < cols; j += nwarps)
+    {
+        const T* a = A + j * lda;
+        C acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            acc[v] = czero<C>();
+        long long i = lane;
+        for (; i + 96 < rows; i += 128)
+        {
+            C av[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                av[u] = cconj(widen(a[i + 32 * u]));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    acc[v] = cadd(acc[v], cmul(av[u], (C)widen(X[i + 32 * u + v * ldx])));
+        }
+        for (; i < rows; i += 32)
+        {
+            const C av = cconj(widen(a[i]));
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                acc[v] = cadd(acc[v], cmul(av, (C)widen(X[i + v * ldx])));
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+        {
+            C r;
+            if constexpr (Traits<T>::cplx)
+                r = cxd{warp_sum(acc[v].re), warp_sum(acc[v].im)};
+            else
+                r = warp_sum(acc[v]);
+            if (lane == 0)
+                Y[j + v * ldy] = narrow<T>(r);
+        }
+    }
+}
+
+// One Lanczos step for vector blockIdx.x (reference: cpu/lanczos.hpp:93-150,
+// cuda/lanczos.hpp:178-262):
+//   alpha = <v1, v2>; v2 -= alpha v1; d[k] = Re alpha;
+//   if k > 0: v2 -= beta_prev v0;  beta = ||v2||;
+//   if k < M-1: v2 *= 1/beta; e[k] = beta
+// scalars live on the device: d, e are M x numvec (column per vector), rbeta[numvec]
+template <class T>
+__global__ void __launch_bounds__(1024) lanczos_step_kernel(long long rows, int k, int M, const T* v0, const T* v1,
+                                                             T* v2, long long ld, double* d, double* e, double* rbeta)
+{
+    using C = typename Traits<T>::comp;
+    using R = typename Traits<T>::real;
+    __shared__ double sh[32];
+    const int vi = blockIdx.x;
+    const T* x0 = v0 + (long long)vi * ld;
+    const T* x1 = v1 + (long long)vi * ld;
+    T* x2 = v2 + (long long)vi * ld;
+    C acc = czero<C>();
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+        acc = cadd(acc, cmul(cconj((C)widen(x1[i])), (C)widen(x2[i])));
+    C alpha;
+    if constexpr (Traits<T>::cplx)
+    {
+        const double re = block_sum(acc.re, sh);
+        const double im = block_sum(acc.im, sh);
+        alpha = narrow_round<T>(cxd{re, im});
+    }
+    else
+    {
+        alpha = narrow_round<T>(block_sum(acc, sh));
+    }
+    const double bprev = (k > 0) ? (double)(R)rbeta[vi] : 0.0;
+    double nrm2 = 0.0;
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+    {
+        C w = csub((C)widen(x2[i]), cmul(alpha, (C)widen(x1[i])));
+        if (k > 0)
+            w = csub(w, cmul(bprev, (C)widen(x0[i])));
+        const T wt = narrow<T>(w);
+        x2[i] = wt;
+        nrm2 += cabs2(widen(wt));
+    }
+    nrm2 = block_sum(nrm2, sh);
+    const R beta = (R)sqrt(nrm2);
+    if (threadIdx.x == 0)
+    {
+        d[k + (long long)M * vi] = creal(alpha);
+        rbeta[vi] = (double)beta;
+        if (k < M - 1)
+            e[k + (long long)M * vi] = (double)beta;
+    }
+    if (k < M - 1)
+    {
+        const double inv = (double)(R)(1 / beta);
+        for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+            x2[i] = narrow<T>(cmul(inv, (C)widen(x2[i])));
+    }
+}
+
+// ---- Philox4x32-10 + Box-Muller: production-mode start vectors ----------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2])
+{
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0;
+    c[1] = n1;
+    c[2] = n2;
+    c[3] = n3;
+    k[0] += 0x9E3779B9u;
+    k[1] += 0xBB67AE85u;
+}
+
+__device__ __forceinline__ void philox_normal2(unsigned long long seed, unsigned long long idx, double& n0, double& n1)
+{
+    uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r)
+        philox_round(c, k);
+    const double u0 = ((double)(((unsigned long long)c[0] << 21) ^ (c[1] >> 11)) + 1.0) * (1.0 / 9007199254740993.0);
+    const double u1 = ((double)(((unsigned long long)c[2] << 21) ^ (c[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+    const double rad = sqrt(-2.0 * log(u0));
+    double sn, cs;
+    sincospi(2.0 * u1, &sn, &cs);
+    n0 = rad * cs;
+    n1 = rad * sn;
+}
+
+template <class T>
+__global__ void rng_normal_kernel(long long rows, long long cols, T* X, long long ldx, unsigned long long seed)
+{
+    const long long total = rows * cols;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x)
+    {
+        double a, b;
+        philox_normal2(seed, (unsigned long long)idx, a, b);
+        const long long i = idx % rows, j = idx / rows;
+        if constexpr (Traits<T>::cplx)
+            X[i + j * ldx] = narrow<T>(cxd{a, b});
+        else
+            X[i + j * ldx] = narrow<T>(a);
+    }
+}
+
+// count entries with |A_ij - conj(A_ji)| > tol * (|A_ij| + |A_ji|) ; also used by isSym
+template <class T>
+__global__ void herm_check_kernel(long long n, const T* A, long long lda, double tol, unsigned long long* bad)
+{
+    const long long total = n * n;
+    unsigned long long cnt = 0;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x)
+    {
+        const long long i = idx % n, j = idx / n;
+        if (i < j)
+            continue;
+        const auto a = widen(A[i + j * lda]);
+        const auto b = cconj(widen(A[j + i * lda]));
+        const double df = sqrt(cabs2(csub(a, b)));
+        if (df > tol * (sqrt(cabs2(a)) + sqrt(cabs2(b))))
+            ++cnt;
+    }
+    if (cnt)
+        atomicAdd(bad, cnt);
+}
+
+template <class T>
+__global__ void shift_diag_kernel(long long n, T* A, long long lda, double c)
+{
+    using C = typename Traits<T>::comp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        A[i + i * lda] = narrow<T>(cadd((C)widen(A[i + i * lda]), from_real<C>(c)));
+}
+
+// A <- upper or lower triangle mirrored to the other one (symOrHermMatrix)
+template <class T>
+__global__ void herm_mirror_kernel(long long n, T* A, long long lda, int from_upper)
+{
+    const long long total = n * n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x)
+    {
+        const long long i = idx % n, j = idx / n;
+        if (i <= j)
+            continue; // (i, j) strictly lower
+        if (from_upper)
+            A[i + j * lda] = narrow<T>(cconj(widen(A[j + i * lda])));
+        else
+            A[j + i * lda] = narrow<T>(cconj(widen(A[i + j * lda])));
+    }
+}
+
+} // namespace cb2

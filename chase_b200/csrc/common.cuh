@@ -1,0 +1,199 @@
+// chase_b200 — shared device-side helpers (sm_100a only).
+//
+// Scalar model: the four ChASE value types s/d/c/z are stored exactly like the
+// reference stores them (float, double, std::complex<float>, std::complex<double>;
+// /root/reference/algorithm/types.hpp:32-120).  All GEMM-shaped kernels compute
+// in FP64 (real or complex) on the DMMA pipe; FP32 storage types are widened on
+// the way into shared memory and rounded once on the way out.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace cb2
+{
+
+template <class R>
+struct cx
+{
+    R re, im;
+};
+using cxf = cx<float>;
+using cxd = cx<double>;
+
+template <class T>
+struct Traits;
+template <>
+struct Traits<float>
+{
+    using real = float;
+    using comp = double; // compute type
+    static constexpr bool cplx = false;
+    static constexpr int code = 0;
+};
+template <>
+struct Traits<double>
+{
+    using real = double;
+    using comp = double;
+    static constexpr bool cplx = false;
+    static constexpr int code = 1;
+};
+template <>
+struct Traits<cxf>
+{
+    using real = float;
+    using comp = cxd;
+    static constexpr bool cplx = true;
+    static constexpr int code = 2;
+};
+template <>
+struct Traits<cxd>
+{
+    using real = double;
+    using comp = cxd;
+    static constexpr bool cplx = true;
+    static constexpr int code = 3;
+};
+
+// ---- arithmetic on the compute types (double / cxd) -------------------------
+__host__ __device__ inline double cmul(double a, double b) { return a * b; }
+__host__ __device__ inline cxd cmul(cxd a, cxd b)
+{
+    return cxd{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__host__ __device__ inline cxd cmul(double a, cxd b) { return cxd{a * b.re, a * b.im}; }
+__host__ __device__ inline double cadd(double a, double b) { return a + b; }
+__host__ __device__ inline cxd cadd(cxd a, cxd b) { return cxd{a.re + b.re, a.im + b.im}; }
+__host__ __device__ inline double csub(double a, double b) { return a - b; }
+__host__ __device__ inline cxd csub(cxd a, cxd b) { return cxd{a.re - b.re, a.im - b.im}; }
+__host__ __device__ inline double cconj(double a) { return a; }
+__host__ __device__ inline cxd cconj(cxd a) { return cxd{a.re, -a.im}; }
+__host__ __device__ inline double cabs2(double a) { return a * a; }
+__host__ __device__ inline double cabs2(cxd a) { return a.re * a.re + a.im * a.im; }
+__host__ __device__ inline double creal(double a) { return a; }
+__host__ __device__ inline double creal(cxd a) { return a.re; }
+__host__ __device__ inline bool cnonzero(double a) { return a != 0.0; }
+__host__ __device__ inline bool cnonzero(cxd a) { return a.re != 0.0 || a.im != 0.0; }
+
+template <class C>
+__host__ __device__ inline C czero();
+template <>
+__host__ __device__ inline double czero<double>()
+{
+    return 0.0;
+}
+template <>
+__host__ __device__ inline cxd czero<cxd>()
+{
+    return cxd{0.0, 0.0};
+}
+template <class C>
+__host__ __device__ inline C from_real(double r);
+template <>
+__host__ __device__ inline double from_real<double>(double r)
+{
+    return r;
+}
+template <>
+__host__ __device__ inline cxd from_real<cxd>(double r)
+{
+    return cxd{r, 0.0};
+}
+
+// widen storage -> compute, narrow compute -> storage
+__host__ __device__ inline double widen(float a) { return (double)a; }
+__host__ __device__ inline double widen(double a) { return a; }
+__host__ __device__ inline cxd widen(cxf a) { return cxd{(double)a.re, (double)a.im}; }
+__host__ __device__ inline cxd widen(cxd a) { return a; }
+template <class T>
+__host__ __device__ inline T narrow(double a);
+template <>
+__host__ __device__ inline float narrow<float>(double a)
+{
+    return (float)a;
+}
+template <>
+__host__ __device__ inline double narrow<double>(double a)
+{
+    return a;
+}
+template <class T>
+__host__ __device__ inline T narrow(cxd a);
+template <>
+__host__ __device__ inline cxf narrow<cxf>(cxd a)
+{
+    return cxf{(float)a.re, (float)a.im};
+}
+template <>
+__host__ __device__ inline cxd narrow<cxd>(cxd a)
+{
+    return a;
+}
+
+// round a compute-type value to the storage precision (keeps the compute type)
+template <class T>
+__host__ __device__ inline typename Traits<T>::comp narrow_round(typename Traits<T>::comp a)
+{
+    return widen(narrow<T>(a));
+}
+
+// scalars cross the C ABI as (re, im) doubles
+template <class C>
+__host__ __device__ inline C make_comp(double re, double im);
+template <>
+__host__ __device__ inline double make_comp<double>(double re, double)
+{
+    return re;
+}
+template <>
+__host__ __device__ inline cxd make_comp<cxd>(double re, double im)
+{
+    return cxd{re, im};
+}
+
+// ---- FP64 tensor-core primitive ------------------------------------------------
+// D(8x8) += A(8x4,row) * B(4x8,col); lane l holds A[l/4][l%4], B[l%4][l/4],
+// D[l/4][2*(l%4)+{0,1}].  Assembles to SASS DMMA.8x8x4 on sm_100a.
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum; every thread gets the result. `sh` needs 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0)
+        sh[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double r = (lane < nw) ? sh[lane] : 0.0;
+    r = warp_sum(r);
+    return r;
+}
+
+} // namespace cb2
+
+#define CB2_CUDA_OK(call)                                                                                              \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess)                                                                                        \
+        {                                                                                                              \
+            std::fprintf(stderr, "chase_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return -1;                                                                                                 \
+        }                                                                                                              \
+    } while (0)

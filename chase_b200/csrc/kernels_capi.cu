@@ -1,0 +1,525 @@
+// chase_b200 — extern "C" launchers for include/chase_b200_kernels.h
+#include "../../include/chase_b200_kernels.h"
+#include "aux.cuh"
+#include "common.cuh"
+#include "factor.cuh"
+#include "gemm_generic.cuh"
+#include "hemm_tma.cuh"
+#include "jacobi.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+using namespace cb2;
+
+namespace
+{
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <class T>
+int gemm_impl(int ta, int tb, int64_t M, int64_t N, int64_t K, double are, double aim, const void* A, int64_t lda,
+              const void* B, int64_t ldb, double bre, double bim, void* C, int64_t ldc, int uplo, void* ws,
+              size_t ws_bytes, void* stream)
+{
+    using C_ = typename Traits<T>::comp;
+    if (M < 0 || N < 0 || K < 0)
+        return -2;
+    GemmArgs<T> p{};
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.A = (const T*)A;
+    p.lda = lda;
+    p.B = (const T*)B;
+    p.ldb = ldb;
+    p.C = (T*)C;
+    p.ldc = ldc;
+    p.alpha = make_comp<C_>(are, aim);
+    p.beta = make_comp<C_>(bre, bim);
+    p.E = nullptr;
+    p.lde = 0;
+    p.gscale = czero<C_>();
+    p.gvec = nullptr;
+    p.uplo = uplo;
+    return gemm_launch<T>(ta != 0, tb != 0, p, ws, ws_bytes, S(stream));
+}
+
+template <class T>
+int hemm_impl(int64_t n, int64_t k, double are, double aim, const void* A, int64_t lda, const void* B, int64_t ldb,
+              double bre, double bim, void* C, int64_t ldc, double shift, const double* theta, void* stream)
+{
+    using C_ = typename Traits<T>::comp;
+    if (n < 0 || k < 0)
+        return -2;
+    if (k == 0 || n == 0)
+        return 0;
+    const C_ alpha = make_comp<C_>(are, aim), beta = make_comp<C_>(bre, bim);
+    if (hemm_tma_supported<T>(n, k, A, lda, B, ldb, C, ldc))
+        return hemm_tma_launch<T>(n, k, alpha, (const T*)A, lda, (const T*)B, ldb, beta, (T*)C, ldc, shift, theta,
+                                  S(stream));
+    GemmArgs<T> p{};
+    p.M = n;
+    p.N = k;
+    p.K = n;
+    p.A = (const T*)A;
+    p.lda = lda;
+    p.B = (const T*)B;
+    p.ldb = ldb;
+    p.C = (T*)C;
+    p.ldc = ldc;
+    p.alpha = alpha;
+    p.beta = beta;
+    p.uplo = 0;
+    if (theta)
+    {
+        p.E = (const T*)B;
+        p.lde = ldb;
+        p.gvec = theta;
+        p.gscale = cmul(-1.0, alpha);
+    }
+    else if (shift != 0.0)
+    {
+        p.E = (const T*)B;
+        p.lde = ldb;
+        p.gvec = nullptr;
+        p.gscale = cmul(-shift, alpha);
+    }
+    return gemm_launch<T>(false, false, p, nullptr, 0, S(stream));
+}
+
+template <class T>
+int potrf_impl(int64_t n, void* Gv, int64_t ldg, int* info_dev, void* stream)
+{
+    using C_ = typename Traits<T>::comp;
+    T* G = (T*)Gv;
+    cudaStream_t st = S(stream);
+    for (int64_t j0 = 0; j0 < n; j0 += POTRF_NB)
+    {
+        const int nb = (int)std::min<int64_t>(POTRF_NB, n - j0);
+        potrf_diag_kernel<T><<<1, 256, 0, st>>>(nb, G, ldg, (int)j0, info_dev);
+        const int64_t rem = n - j0 - nb;
+        if (rem > 0)
+        {
+            potrf_panel_kernel<T><<<(unsigned)((rem + 127) / 128), 128, 0, st>>>((int)n, nb, G, ldg, (int)j0, info_dev);
+            // G[j0+nb:, j0+nb:] -= R[j0:j0+nb, j0+nb:]^H R[j0:j0+nb, j0+nb:]   (upper tiles)
+            GemmArgs<T> p{};
+            p.M = rem;
+            p.N = rem;
+            p.K = nb;
+            p.A = G + j0 + (j0 + nb) * ldg;
+            p.lda = ldg;
+            p.B = G + j0 + (j0 + nb) * ldg;
+            p.ldb = ldg;
+            p.C = G + (j0 + nb) + (j0 + nb) * ldg;
+            p.ldc = ldg;
+            p.alpha = from_real<C_>(-1.0);
+            p.beta = from_real<C_>(1.0);
+            p.uplo = 1;
+            int rc = gemm_launch<T>(true, false, p, nullptr, 0, st);
+            if (rc)
+                return rc;
+        }
+    }
+    CB2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+constexpr int TRSM_NB = 128;
+
+template <class T>
+int trsm_impl(int64_t rows, int64_t n, const void* Rv, int64_t ldr, void* Vv, int64_t ldv, void* Xv, int64_t ldx,
+              void* ws, size_t ws_bytes, void* stream)
+{
+    using C_ = typename Traits<T>::comp;
+    if (n == 0 || rows == 0)
+        return 0;
+    const int64_t nblk = (n + TRSM_NB - 1) / TRSM_NB;
+    if (ws_bytes < (size_t)nblk * TRSM_NB * TRSM_NB * sizeof(T))
+        return -3;
+    const T* Rm = (const T*)Rv;
+    T* V = (T*)Vv;
+    T* X = (T*)Xv;
+    T* Rinv = (T*)ws;
+    cudaStream_t st = S(stream);
+    trinv_kernel<T><<<(unsigned)nblk, TRSM_NB, 0, st>>>((int)n, TRSM_NB, Rm, ldr, Rinv);
+    CB2_CUDA_OK(cudaGetLastError());
+    for (int64_t b = 0; b < nblk; ++b)
+    {
+        const int64_t j0 = b * TRSM_NB;
+        const int64_t nb = std::min<int64_t>(TRSM_NB, n - j0);
+        GemmArgs<T> p{};
+        if (b > 0)
+        {
+            // V_b -= X[:, :j0] R[:j0, j0:j0+nb]
+            p.M = rows;
+            p.N = nb;
+            p.K = j0;
+            p.A = X;
+            p.lda = ldx;
+            p.B = Rm + j0 * ldr;
+            p.ldb = ldr;
+            p.C = V + j0 * ldv;
+            p.ldc = ldv;
+            p.alpha = from_real<C_>(-1.0);
+            p.beta = from_real<C_>(1.0);
+            int rc = gemm_launch<T>(false, false, p, nullptr, 0, st);
+            if (rc)
+                return rc;
+        }
+        // X_b = V_b inv(R_bb)
+        GemmArgs<T> q{};
+        q.M = rows;
+        q.N = nb;
+        q.K = nb;
+        q.A = V + j0 * ldv;
+        q.lda = ldv;
+        q.B = Rinv + b * TRSM_NB * TRSM_NB;
+        q.ldb = TRSM_NB;
+        q.C = X + j0 * ldx;
+        q.ldc = ldx;
+        q.alpha = from_real<C_>(1.0);
+        q.beta = czero<C_>();
+        int rc = gemm_launch<T>(false, false, q, nullptr, 0, st);
+        if (rc)
+            return rc;
+    }
+    return 0;
+}
+
+template <class T>
+int heev_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, double* w_host, void* ws,
+              size_t ws_bytes, int* sweeps_out, void* stream)
+{
+    using C_ = typename Traits<T>::comp;
+    const int n = (int)n64;
+    if (n <= 0)
+        return 0;
+    cudaStream_t st = S(stream);
+    const size_t need = chase_b200_heev_ws_bytes(n, Traits<T>::cplx);
+    if (ws_bytes < need)
+        return -3;
+    // workspace layout: Gw | Zw | rots | w | perm | fro2 | nrot
+    unsigned char* base = (unsigned char*)ws;
+    C_* Gw = (C_*)base;
+    C_* Zw = Gw + (size_t)n * n;
+    size_t off = 2 * (size_t)n * n * sizeof(C_);
+    const int np = (n + 1) & ~1, h = np / 2;
+    JRot* rots = (JRot*)(base + off);
+    off += (size_t)h * sizeof(JRot);
+    off = (off + 15) & ~(size_t)15;
+    double* w_dev = (double*)(base + off);
+    off += (size_t)n * sizeof(double);
+    double* fro2 = (double*)(base + off);
+    off += 16;
+    int* nrot = (int*)(base + off);
+    off += 16;
+    int* perm_dev = (int*)(base + off);
+
+    CB2_CUDA_OK(cudaMemsetAsync(fro2, 0, 32, st));
+    {
+        const long long total = (long long)n * n;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 2368);
+        jacobi_init_kernel<T><<<blocks, 256, 0, st>>>(n, (const T*)Gv, ldg, Gw, Zw, fro2);
+    }
+    int sweep = 0, converged = 0;
+    const int max_sweeps = 40;
+    const dim3 agrid((unsigned)((std::max(n, h) + 127) / 128), (unsigned)h, 2);
+    for (; sweep < max_sweeps; ++sweep)
+    {
+        CB2_CUDA_OK(cudaMemsetAsync(nrot, 0, sizeof(int), st));
+        for (int r = 0; r < np - 1; ++r)
+        {
+            jacobi_rot_kernel<C_><<<(h + 127) / 128, 128, 0, st>>>(n, np, r, Gw, rots, fro2, nrot);
+            jacobi_apply_kernel<C_><<<agrid, 128, 0, st>>>(n, np, r, Gw, Zw, rots);
+        }
+        int nr = 0;
+        CB2_CUDA_OK(cudaMemcpyAsync(&nr, nrot, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CB2_CUDA_OK(cudaStreamSynchronize(st));
+        if (nr == 0)
+        {
+            converged = 1;
+            break;
+        }
+    }
+    jacobi_diag_kernel<C_><<<(n + 255) / 256, 256, 0, st>>>(n, Gw, w_dev);
+    std::vector<double> w(n);
+    CB2_CUDA_OK(cudaMemcpyAsync(w.data(), w_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CB2_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<int> perm(n);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return w[a] < w[b]; });
+    for (int i = 0; i < n; ++i)
+        w_host[i] = w[perm[i]];
+    CB2_CUDA_OK(cudaMemcpyAsync(perm_dev, perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    jacobi_gather_kernel<T><<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, st>>>(n, Zw, perm_dev, (T*)Zv, ldz);
+    CB2_CUDA_OK(cudaGetLastError());
+    CB2_CUDA_OK(cudaStreamSynchronize(st)); // perm (host vector) must outlive the copy
+    if (sweeps_out)
+        *sweeps_out = sweep + (converged ? 1 : 0);
+    return converged ? 0 : 1;
+}
+
+template <class T>
+int gemv_impl(int64_t rows, int64_t cols, const void* A, int64_t lda, const void* X, int64_t ldx, int nv, void* Y,
+              int64_t ldy, void* stream)
+{
+    cudaStream_t st = S(stream);
+    if (rows <= 0 || cols <= 0 || nv <= 0)
+        return 0;
+    const int blocks = (int)std::min<int64_t>((cols + 7) / 8, 148 * 8);
+    int v = 0;
+    while (v < nv)
+    {
+        const T* x = (const T*)X + (int64_t)v * ldx;
+        T* y = (T*)Y + (int64_t)v * ldy;
+        if (nv - v >= 4)
+        {
+            gemv_conjT_kernel<T, 4><<<blocks, 256, 0, st>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
+            v += 4;
+        }
+        else if (nv - v >= 2)
+        {
+            gemv_conjT_kernel<T, 2><<<blocks, 256, 0, st>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
+            v += 2;
+        }
+        else
+        {
+            gemv_conjT_kernel<T, 1><<<blocks, 256, 0, st>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
+            v += 1;
+        }
+    }
+    CB2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+inline dim3 grid2d(int64_t rows, int64_t cols)
+{
+    unsigned gx = (unsigned)std::min<int64_t>(std::max<int64_t>((rows + 255) / 256, 1), 64);
+    unsigned gy = (unsigned)std::min<int64_t>(std::max<int64_t>(cols, 1), 65535);
+    return dim3(gx, gy);
+}
+
+// register-resident DMMA loop: 8 independent accumulator pairs per warp
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
+{
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        acc[i][0] = acc[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            dmma884(acc[i][0], acc[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        s += acc[i][0] + acc[i][1];
+    if (s == 12345.678)
+        sink[0] = s;
+}
+
+} // namespace
+
+#define CB2_DEFINE_API(X, TT)                                                                                          \
+    extern "C" int chase_b200_gemm_##X(int ta, int tb, int64_t M, int64_t N, int64_t K, double are, double aim,       \
+                                       const void* A, int64_t lda, const void* B, int64_t ldb, double bre,            \
+                                       double bim, void* C, int64_t ldc, int uplo, void* ws, size_t wsb, void* st)    \
+    {                                                                                                                  \
+        return gemm_impl<TT>(ta, tb, M, N, K, are, aim, A, lda, B, ldb, bre, bim, C, ldc, uplo, ws, wsb, st);         \
+    }                                                                                                                  \
+    extern "C" int chase_b200_hemm_##X(int64_t n, int64_t k, double are, double aim, const void* A, int64_t lda,      \
+                                       const void* B, int64_t ldb, double bre, double bim, void* C, int64_t ldc,      \
+                                       double shift, const double* theta, void* st)                                   \
+    {                                                                                                                  \
+        return hemm_impl<TT>(n, k, are, aim, A, lda, B, ldb, bre, bim, C, ldc, shift, theta, st);                     \
+    }                                                                                                                  \
+    extern "C" int chase_b200_potrf_##X(int64_t n, void* G, int64_t ldg, int* info, void* st)                         \
+    {                                                                                                                  \
+        return potrf_impl<TT>(n, G, ldg, info, st);                                                                    \
+    }                                                                                                                  \
+    extern "C" int chase_b200_trsm_##X(int64_t rows, int64_t n, const void* R, int64_t ldr, void* V, int64_t ldv,     \
+                                       void* Xo, int64_t ldx, void* ws, size_t wsb, void* st)                         \
+    {                                                                                                                  \
+        return trsm_impl<TT>(rows, n, R, ldr, V, ldv, Xo, ldx, ws, wsb, st);                                          \
+    }                                                                                                                  \
+    extern "C" int chase_b200_shift_abstrace_##X(int64_t n, void* G, int64_t ldg, double scale, double* so, void* st) \
+    {                                                                                                                  \
+        if (n <= 0)                                                                                                    \
+            return 0;                                                                                                  \
+        shift_by_abstrace_kernel<TT><<<1, 256, 0, S(st)>>>((int)n, (TT*)G, ldg, scale, so);                           \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_heev_##X(int64_t n, const void* G, int64_t ldg, void* Z, int64_t ldz, double* w,        \
+                                       void* ws, size_t wsb, int* sweeps, void* st)                                   \
+    {                                                                                                                  \
+        return heev_impl<TT>(n, G, ldg, Z, ldz, w, ws, wsb, sweeps, st);                                              \
+    }                                                                                                                  \
+    extern "C" int chase_b200_colnorms_##X(int64_t rows, int64_t cols, const void* Xm, int64_t ldx, double* out,      \
+                                           int take_sqrt, void* st)                                                   \
+    {                                                                                                                  \
+        if (cols <= 0)                                                                                                 \
+            return 0;                                                                                                  \
+        colnorm_kernel<TT><<<(unsigned)cols, 256, 0, S(st)>>>(rows, (const TT*)Xm, ldx, out, take_sqrt);              \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_lacpy_##X(int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst,          \
+                                        int64_t ldd, void* st)                                                        \
+    {                                                                                                                  \
+        if (rows <= 0 || cols <= 0)                                                                                    \
+            return 0;                                                                                                  \
+        lacpy_kernel<TT><<<grid2d(rows, cols), 256, 0, S(st)>>>(rows, cols, (const TT*)src, lds, (TT*)dst, ldd);      \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_gather_cols_##X(int64_t rows, int cnt, const int* sc, const int* dc, const void* src,   \
+                                              int64_t lds, void* dst, int64_t ldd, void* st)                          \
+    {                                                                                                                  \
+        if (rows <= 0 || cnt <= 0)                                                                                     \
+            return 0;                                                                                                  \
+        gather_cols_kernel<TT><<<grid2d(rows, cnt), 256, 0, S(st)>>>(rows, cnt, sc, dc, (const TT*)src, lds,          \
+                                                                      (TT*)dst, ldd);                                  \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_gemv_conjt_##X(int64_t rows, int64_t cols, const void* A, int64_t lda, const void* Xm,  \
+                                             int64_t ldx, int nv, void* Y, int64_t ldy, void* st)                     \
+    {                                                                                                                  \
+        return gemv_impl<TT>(rows, cols, A, lda, Xm, ldx, nv, Y, ldy, st);                                            \
+    }                                                                                                                  \
+    extern "C" int chase_b200_lanczos_step_##X(int64_t rows, int nv, int k, int M, const void* v0, const void* v1,    \
+                                               void* v2, int64_t ld, double* d, double* e, double* rb, void* st)      \
+    {                                                                                                                  \
+        if (nv <= 0)                                                                                                   \
+            return 0;                                                                                                  \
+        lanczos_step_kernel<TT><<<nv, 1024, 0, S(st)>>>(rows, k, M, (const TT*)v0, (const TT*)v1, (TT*)v2, ld, d, e,  \
+                                                        rb);                                                           \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_normalize_cols_##X(int64_t rows, int64_t cols, void* Xm, int64_t ldx, void* st)         \
+    {                                                                                                                  \
+        if (cols <= 0)                                                                                                 \
+            return 0;                                                                                                  \
+        normalize_cols_kernel<TT><<<(unsigned)cols, 1024, 0, S(st)>>>(rows, (TT*)Xm, ldx);                            \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_rng_normal_##X(int64_t rows, int64_t cols, void* Xm, int64_t ldx, uint64_t seed,        \
+                                             void* st)                                                                \
+    {                                                                                                                  \
+        if (rows <= 0 || cols <= 0)                                                                                    \
+            return 0;                                                                                                  \
+        rng_normal_kernel<TT><<<1184, 256, 0, S(st)>>>(rows, cols, (TT*)Xm, ldx, seed);                               \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_herm_check_##X(int64_t n, const void* A, int64_t lda, double tol,                       \
+                                             unsigned long long* bad, void* st)                                       \
+    {                                                                                                                  \
+        if (n <= 0)                                                                                                    \
+            return 0;                                                                                                  \
+        herm_check_kernel<TT><<<1184, 256, 0, S(st)>>>(n, (const TT*)A, lda, tol, bad);                               \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_shift_diag_##X(int64_t n, void* A, int64_t lda, double c, void* st)                     \
+    {                                                                                                                  \
+        if (n <= 0)                                                                                                    \
+            return 0;                                                                                                  \
+        shift_diag_kernel<TT><<<(unsigned)((n + 255) / 256), 256, 0, S(st)>>>(n, (TT*)A, lda, c);                     \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_herm_mirror_##X(int64_t n, void* A, int64_t lda, int from_upper, void* st)              \
+    {                                                                                                                  \
+        if (n <= 0)                                                                                                    \
+            return 0;                                                                                                  \
+        herm_mirror_kernel<TT><<<1184, 256, 0, S(st)>>>(n, (TT*)A, lda, from_upper);                                  \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }
+
+CB2_DEFINE_API(s, float)
+CB2_DEFINE_API(d, double)
+CB2_DEFINE_API(c, cxf)
+CB2_DEFINE_API(z, cxd)
+
+extern "C" int chase_b200_tridiag_eig(int n, int batch, const double* d, const double* e, int ldde, double* w,
+                                      double* Z, void* st)
+{
+    if (n <= 0 || batch <= 0)
+        return 0;
+    if (n > JSMALL_MAX)
+        return -2;
+    jacobi_small_tridiag_kernel<<<batch, 256, 0, S(st)>>>(n, d, e, ldde, w, Z, nullptr);
+    CB2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" size_t chase_b200_trsm_ws_bytes(int64_t n, int elem_bytes)
+{
+    const int64_t nblk = (n + TRSM_NB - 1) / TRSM_NB;
+    return (size_t)nblk * TRSM_NB * TRSM_NB * (size_t)elem_bytes;
+}
+
+extern "C" size_t chase_b200_heev_ws_bytes(int64_t n, int is_complex)
+{
+    const size_t ce = is_complex ? 16 : 8;
+    const size_t np = (size_t)((n + 1) & ~(int64_t)1);
+    size_t b = 2 * (size_t)n * n * ce;
+    b += (np / 2) * sizeof(JRot) + 16;
+    b += (size_t)n * sizeof(double) + 32;
+    b += (size_t)n * sizeof(int) + 64;
+    return b;
+}
+
+extern "C" int chase_b200_hemm_path(int code, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc)
+{
+    // pointers are assumed 128-byte aligned here (the solver's own buffers are)
+    const void* al = reinterpret_cast<const void*>(uintptr_t(1024));
+    switch (code)
+    {
+        case 0: return hemm_tma_supported<float>(n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
+        case 1: return hemm_tma_supported<double>(n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
+        case 2: return hemm_tma_supported<cxf>(n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
+        case 3: return hemm_tma_supported<cxd>(n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
+    }
+    return 0;
+}
+
+extern "C" double chase_b200_dmma_peak(int iters, void* st)
+{
+    cudaStream_t s = S(st);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess)
+        return -1.0;
+    const int blocks = sms * 4;
+    dmma_peak_kernel<<<blocks, 256, 0, s>>>(iters / 4 + 1, sink); // warm-up
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    dmma_peak_kernel<<<blocks, 256, 0, s>>>(iters, sink);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    const double flops = 2.0 * 8 * 8 * 4 * 8.0 * (double)iters * 8.0 * blocks; // per DMMA 512 flop, 8/iter/warp, 8 warps
+    return flops / (ms * 1e-3);
+}
+
+extern "C" const char* chase_b200_version(void) { return "chase_b200 0.1 (sm_100a)"; }

@@ -1,0 +1,400 @@
+// chase_b200 — implementation of include/chase_c_interface.h.
+// Mirrors the reference's sequential C interface
+// (interface/chase_c_interface.cpp:105-150 Initialize, :443-466 solve wrapper,
+// :493-513 copy_first_nev_results, :3804-... unified setters): one
+// process-global solver per scalar type, wrapped in the performance decorator
+// for every solve.
+#include "../../include/chase_c_interface.h"
+
+#include "algorithm.hpp"
+#include "chase_gpu.hpp"
+#include "performance.hpp"
+
+#include <complex>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+extern "C" int chase_b200_device_sync(void) { return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1; }
+
+namespace
+{
+
+struct LastRun
+{
+    double stats[16] = {0};
+    std::string trace;
+    std::string qr_log;
+    std::string error;
+};
+LastRun g_last;
+bool g_trace = false;
+
+template <class T>
+struct Seq
+{
+    using R = chase::Base<T>;
+    std::unique_ptr<chase::Impl::ChASEGPU<T>> solver;
+    std::vector<T> vec;   // internal V when the caller passed NULL
+    std::vector<R> ritz;  // internal ritzv when the caller passed NULL
+    T* V = nullptr;
+    R* ritzv = nullptr;
+    std::size_t N = 0;
+
+    static Seq& get()
+    {
+        static Seq s;
+        return s;
+    }
+    int init(int N_, int nev, int nex, T* H, int ldh, T* V_, R* ritzv_)
+    {
+        solver.reset();
+        N = (std::size_t)N_;
+        V = V_;
+        if (V == nullptr)
+        {
+            vec.assign((std::size_t)N_ * (std::size_t)(nev + nex), T(0));
+            V = vec.data();
+        }
+        ritzv = ritzv_;
+        if (ritzv == nullptr)
+        {
+            ritz.assign((std::size_t)(nev + nex), R(0));
+            ritzv = ritz.data();
+        }
+        try
+        {
+            solver.reset(new chase::Impl::ChASEGPU<T>((std::size_t)N_, (std::size_t)nev, (std::size_t)nex, H,
+                                                      (std::size_t)ldh, V, (std::size_t)N_, ritzv));
+        }
+        catch (const std::exception& e)
+        {
+            std::fprintf(stderr, "chase_b200: init failed: %s\n", e.what());
+            g_last.error = e.what();
+            return 0;
+        }
+        return 1;
+    }
+    void finalize()
+    {
+        solver.reset();
+        std::vector<T>().swap(vec);
+        std::vector<R>().swap(ritz);
+    }
+    void solve(int deg, R tol, char mode, char opt, char qr)
+    {
+        if (!solver)
+            return;
+        auto& config = solver->GetConfig();
+        config.SetTol(tol);
+        config.SetDeg((std::size_t)deg);
+        config.SetOpt(opt == 'S');
+        config.SetApprox(mode == 'A');
+        config.SetCholQR(qr == 'C');
+        solver->clear_logs();
+        chase::PerformanceDecoratorChase<T> perf(solver.get());
+        perf.EnableTrace(g_trace);
+        g_last.error.clear();
+        try
+        {
+            chase::Solve(&perf);
+        }
+        catch (const std::exception& e)
+        {
+            // C callers cannot catch: report, flag (stats[15] = 1) and return
+            std::fprintf(stderr, "chase_b200: solve failed: %s\n", e.what());
+            g_last.error = e.what();
+        }
+
+        auto& pd = perf.GetPerfData();
+        const int factor = chase::is_complex_t<T>::value ? 4 : 1;
+        double* s = g_last.stats;
+        s[0] = (double)pd.get_iter_count();
+        s[1] = (double)pd.get_filtered_vecs();
+        s[2] = (double)perf.HemmCalls();
+        s[3] = (double)perf.Swaps();
+        s[4] = pd.seconds(chase::ChasePerfData::All);
+        s[5] = pd.seconds(chase::ChasePerfData::InitVecs);
+        s[6] = pd.seconds(chase::ChasePerfData::Lanczos);
+        s[7] = pd.seconds(chase::ChasePerfData::Filter);
+        s[8] = pd.seconds(chase::ChasePerfData::Qr);
+        s[9] = pd.seconds(chase::ChasePerfData::Rr);
+        s[10] = pd.seconds(chase::ChasePerfData::Resid);
+        s[11] = pd.get_filter_flops(N, factor);
+        s[12] = pd.get_flops(N, config.GetLanczosIter(), config.GetNumLanczos(), factor);
+        s[13] = (double)solver->heev_sweeps();
+        s[14] = (double)solver->gather_passes();
+        s[15] = g_last.error.empty() ? 0.0 : 1.0;
+        g_last.trace.clear();
+        for (auto& l : perf.Trace())
+        {
+            g_last.trace += l;
+            g_last.trace += '\n';
+        }
+        g_last.qr_log.clear();
+        for (auto& l : solver->qr_log())
+        {
+            g_last.qr_log += l;
+            g_last.qr_log += '\n';
+        }
+        if (std::getenv("CHASE_B200_VERBOSE"))
+            pd.print(N, factor);
+    }
+    void get_eigenpairs(T* out, int ld, R* ritz_out)
+    {
+        if (!solver || out == nullptr || ritz_out == nullptr || ld <= 0)
+            return;
+        const std::size_t nev = solver->GetNev();
+        for (std::size_t j = 0; j < nev; ++j)
+            std::memcpy(out + j * (std::size_t)ld, V + j * N, N * sizeof(T));
+        std::memcpy(ritz_out, ritzv, nev * sizeof(R));
+    }
+    void get_resid(R* out)
+    {
+        if (!solver || !out)
+            return;
+        const std::size_t nevex = solver->GetNev() + solver->GetNex();
+        std::memcpy(out, solver->GetResid(), nevex * sizeof(R));
+    }
+};
+
+using SD = Seq<double>;
+using SS = Seq<float>;
+using SZ = Seq<std::complex<double>>;
+using SC = Seq<std::complex<float>>;
+
+template <class F>
+void with_active_config(F&& f)
+{
+    if (SD::get().solver)
+        f(SD::get().solver->GetConfig());
+    else if (SS::get().solver)
+        f(SS::get().solver->GetConfig());
+    else if (SZ::get().solver)
+        f(SZ::get().solver->GetConfig());
+    else if (SC::get().solver)
+        f(SC::get().solver->GetConfig());
+}
+
+size_t copy_out(const std::string& s, char* buf, size_t cap)
+{
+    if (buf && cap > 0)
+    {
+        const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return s.size();
+}
+
+} // namespace
+
+extern "C"
+{
+    using cf = std::complex<float>;
+    using cd = std::complex<double>;
+
+    void dchase_init_(int* N, int* nev, int* nex, double* H, int* ldh, double* V, double* ritzv, int* init)
+    {
+        *init = SD::get().init(*N, *nev, *nex, H, *ldh, V, ritzv);
+    }
+    void schase_init_(int* N, int* nev, int* nex, float* H, int* ldh, float* V, float* ritzv, int* init)
+    {
+        *init = SS::get().init(*N, *nev, *nex, H, *ldh, V, ritzv);
+    }
+    void cchase_init_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, CHASE_B200_CF* V, float* ritzv,
+                      int* init)
+    {
+        *init = SC::get().init(*N, *nev, *nex, reinterpret_cast<cf*>(H), *ldh, reinterpret_cast<cf*>(V), ritzv);
+    }
+    void zchase_init_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, CHASE_B200_CD* V, double* ritzv,
+                      int* init)
+    {
+        *init = SZ::get().init(*N, *nev, *nex, reinterpret_cast<cd*>(H), *ldh, reinterpret_cast<cd*>(V), ritzv);
+    }
+    void dchase_init_internal_(int* N, int* nev, int* nex, double* H, int* ldh, int* init)
+    {
+        *init = SD::get().init(*N, *nev, *nex, H, *ldh, nullptr, nullptr);
+    }
+    void schase_init_internal_(int* N, int* nev, int* nex, float* H, int* ldh, int* init)
+    {
+        *init = SS::get().init(*N, *nev, *nex, H, *ldh, nullptr, nullptr);
+    }
+    void cchase_init_internal_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, int* init)
+    {
+        *init = SC::get().init(*N, *nev, *nex, reinterpret_cast<cf*>(H), *ldh, nullptr, nullptr);
+    }
+    void zchase_init_internal_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, int* init)
+    {
+        *init = SZ::get().init(*N, *nev, *nex, reinterpret_cast<cd*>(H), *ldh, nullptr, nullptr);
+    }
+
+    void dchase_finalize_(int* flag)
+    {
+        SD::get().finalize();
+        *flag = 0;
+    }
+    void schase_finalize_(int* flag)
+    {
+        SS::get().finalize();
+        *flag = 0;
+    }
+    void cchase_finalize_(int* flag)
+    {
+        SC::get().finalize();
+        *flag = 0;
+    }
+    void zchase_finalize_(int* flag)
+    {
+        SZ::get().finalize();
+        *flag = 0;
+    }
+
+    void dchase_(int* deg, double* tol, char* mode, char* opt, char* qr)
+    {
+        SD::get().solve(*deg, *tol, *mode, *opt, *qr);
+    }
+    void schase_(int* deg, float* tol, char* mode, char* opt, char* qr)
+    {
+        SS::get().solve(*deg, *tol, *mode, *opt, *qr);
+    }
+    void zchase_(int* deg, double* tol, char* mode, char* opt, char* qr)
+    {
+        SZ::get().solve(*deg, *tol, *mode, *opt, *qr);
+    }
+    void cchase_(int* deg, float* tol, char* mode, char* opt, char* qr)
+    {
+        SC::get().solve(*deg, *tol, *mode, *opt, *qr);
+    }
+
+    void dchase_get_eigenpairs_(double* V, int* ld, double* ritzv)
+    {
+        if (ld)
+            SD::get().get_eigenpairs(V, *ld, ritzv);
+    }
+    void schase_get_eigenpairs_(float* V, int* ld, float* ritzv)
+    {
+        if (ld)
+            SS::get().get_eigenpairs(V, *ld, ritzv);
+    }
+    void cchase_get_eigenpairs_(CHASE_B200_CF* V, int* ld, float* ritzv)
+    {
+        if (ld)
+            SC::get().get_eigenpairs(reinterpret_cast<cf*>(V), *ld, ritzv);
+    }
+    void zchase_get_eigenpairs_(CHASE_B200_CD* V, int* ld, double* ritzv)
+    {
+        if (ld)
+            SZ::get().get_eigenpairs(reinterpret_cast<cd*>(V), *ld, ritzv);
+    }
+
+    void dchase_get_resid_(double* r) { SD::get().get_resid(r); }
+    void schase_get_resid_(float* r) { SS::get().get_resid(r); }
+    void cchase_get_resid_(float* r) { SC::get().get_resid(r); }
+    void zchase_get_resid_(double* r) { SZ::get().get_resid(r); }
+
+    void chase_set_tol_(double* tol)
+    {
+        with_active_config([&](auto& c) { c.SetTol(*tol); });
+    }
+    void chase_set_deg_(int* deg)
+    {
+        with_active_config([&](auto& c) { c.SetDeg((std::size_t)*deg); });
+    }
+    void chase_set_max_deg_(int* v)
+    {
+        with_active_config([&](auto& c) { c.SetMaxDeg((std::size_t)*v); });
+    }
+    void chase_set_deg_extra_(int* v)
+    {
+        with_active_config([&](auto& c) { c.SetDegExtra((std::size_t)*v); });
+    }
+    void chase_set_max_iter_(int* v)
+    {
+        with_active_config([&](auto& c) { c.SetMaxIter((std::size_t)*v); });
+    }
+    void chase_set_lanczos_iter_(int* v)
+    {
+        with_active_config([&](auto& c) { c.SetLanczosIter((std::size_t)*v); });
+    }
+    void chase_set_num_lanczos_(int* v)
+    {
+        with_active_config([&](auto& c) { c.SetNumLanczos((std::size_t)*v); });
+    }
+    void chase_set_approx_(int* flag)
+    {
+        with_active_config([&](auto& c) { c.SetApprox(*flag != 0); });
+    }
+    void chase_set_opt_(int* flag)
+    {
+        with_active_config([&](auto& c) { c.SetOpt(*flag != 0); });
+    }
+    void chase_set_cholqr_(int* flag)
+    {
+        with_active_config([&](auto& c) { c.SetCholQR(*flag != 0); });
+    }
+    void chase_enable_sym_check_(int* flag)
+    {
+        with_active_config([&](auto& c) { c.EnableSymCheck(*flag != 0); });
+    }
+    void chase_set_decaying_rate_(float* v)
+    {
+        with_active_config([&](auto& c) { c.SetDecayingRate(*v); });
+    }
+    void chase_set_cluster_aware_degrees_(int* flag)
+    {
+        with_active_config([&](auto& c) { c.SetClusterAwareDegrees(*flag != 0); });
+    }
+    void chase_set_upperb_scale_rate_(float* v)
+    {
+        with_active_config([&](auto& c) { c.SetUpperbScaleRate(*v); });
+    }
+
+    void chase_get_version_(char* version, int* len)
+    {
+        const char* v = chase_b200_version();
+        if (version && len && *len > 0)
+        {
+            std::strncpy(version, v, (size_t)*len - 1);
+            version[*len - 1] = 0;
+        }
+    }
+    void chase_has_cuda_(int* flag) { *flag = 1; }
+    void chase_has_nccl_(int* flag) { *flag = 0; }
+    void chase_has_scalapack_(int* flag) { *flag = 0; }
+    void chase_has_mpi_(int* flag) { *flag = 0; }
+    void chase_print_config_(void)
+    {
+        std::printf("%s: CUDA yes (hand-written sm_100a kernels, no cuBLAS/cuSOLVER), NCCL no, ScaLAPACK no, MPI no\n",
+                    chase_b200_version());
+    }
+
+    void chase_b200_start_vectors_d(int64_t N, int64_t m, double* V, int64_t ldv)
+    {
+        chase::Impl::fill_start_vectors<double>((size_t)N, (size_t)m, V, (size_t)ldv);
+    }
+    void chase_b200_start_vectors_s(int64_t N, int64_t m, float* V, int64_t ldv)
+    {
+        chase::Impl::fill_start_vectors<float>((size_t)N, (size_t)m, V, (size_t)ldv);
+    }
+    void chase_b200_start_vectors_z(int64_t N, int64_t m, CHASE_B200_CD* V, int64_t ldv)
+    {
+        chase::Impl::fill_start_vectors<cd>((size_t)N, (size_t)m, reinterpret_cast<cd*>(V), (size_t)ldv);
+    }
+    void chase_b200_start_vectors_c(int64_t N, int64_t m, CHASE_B200_CF* V, int64_t ldv)
+    {
+        chase::Impl::fill_start_vectors<cf>((size_t)N, (size_t)m, reinterpret_cast<cf*>(V), (size_t)ldv);
+    }
+
+    void chase_b200_get_stats_(double* out, int* n)
+    {
+        const int cnt = (*n < 16) ? *n : 16;
+        for (int i = 0; i < cnt; ++i)
+            out[i] = g_last.stats[i];
+    }
+    void chase_b200_trace_enable_(int* flag) { g_trace = (*flag != 0); }
+    size_t chase_b200_trace_copy_(char* buf, size_t cap) { return copy_out(g_last.trace, buf, cap); }
+    size_t chase_b200_qr_log_copy_(char* buf, size_t cap) { return copy_out(g_last.qr_log, buf, cap); }
+    size_t chase_b200_last_error_copy_(char* buf, size_t cap) { return copy_out(g_last.error, buf, cap); }
+}

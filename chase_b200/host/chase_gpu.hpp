@@ -1,0 +1,589 @@
+// chase_b200 host layer — single-GPU backend chase::Impl::ChASEGPU<T>.
+//
+// Drop-in for the reference's chase::Impl::ChASEGPU<T, Matrix<T,GPU>>
+// (Impl/chase_gpu/chase_gpu.hpp:107-1080): same constructor
+// (N, nev, nex, H, ldh, V1, ldv, ritzv; caller owns the host buffers), same
+// ChaseBase<T> semantics — HEMM swaps the two panels, RR/Resd write host
+// arrays, Swap takes absolute column indices, End() copies all nev+nex vectors
+// back into the caller's V — but everything below is new:
+//   * A stays immutable on the device; Shift(c) is folded into the HEMM
+//     epilogue (alpha*(A*B - c*B) + beta*C), so no diagonal kernel touches A;
+//   * the O(k^2) Swap storm of calc_degrees/locking is accumulated as a host
+//     permutation and applied as ONE gather pass before the next device op;
+//   * residuals are A*V - V*diag(theta) in a single fused HEMM + column norms;
+//   * every device op is a hand-written sm_100a kernel behind the C ABI of
+//     include/chase_b200_kernels.h (no cuBLAS / cuSOLVER / cuRAND);
+//   * device panels are padded to a 16-element leading dimension (TMA/128-bit
+//     friendly) regardless of the caller's ldh/ldv.
+#pragma once
+#include "algorithm.hpp"
+#include "interface.hpp"
+#include "kernel_api.hpp"
+
+#include <cuda_runtime_api.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace chase
+{
+namespace Impl
+{
+
+#define CB2_CHECK(call)                                                                                                \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess)                                                                                        \
+        {                                                                                                              \
+            std::fprintf(stderr, "chase_b200: CUDA failure '%s' at %s:%d\n", cudaGetErrorString(e__), __FILE__,       \
+                         __LINE__);                                                                                    \
+            std::exit(EXIT_FAILURE);                                                                                   \
+        }                                                                                                              \
+    } while (0)
+
+#define CB2_KCHECK(call)                                                                                               \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        int rc__ = (call);                                                                                             \
+        if (rc__ < 0)                                                                                                  \
+        {                                                                                                              \
+            std::fprintf(stderr, "chase_b200: kernel launcher failed (%d) at %s:%d\n", rc__, __FILE__, __LINE__);     \
+            std::exit(EXIT_FAILURE);                                                                                   \
+        }                                                                                                              \
+    } while (0)
+
+// Start block of the reference CPU backend, bit for bit: std::mt19937(1337) +
+// std::normal_distribution<double>, filled column by column (chase_cpu.hpp:296-309).
+template <class T>
+inline void fill_start_vectors(std::size_t N, std::size_t ncols, T* V, std::size_t ldv)
+{
+    std::mt19937 gen(1337.0);
+    std::normal_distribution<> d;
+    for (std::size_t j = 0; j < ncols; ++j)
+        for (std::size_t i = 0; i < N; ++i)
+            V[i + j * ldv] = getRandomT<T>([&]() { return d(gen); });
+}
+
+template <class T>
+class ChASEGPU : public ChaseBase<T>
+{
+    using R = Base<T>;
+    using KK = b200::K<T>;
+    static constexpr bool kCplx = is_complex_t<T>::value;
+
+public:
+    ChASEGPU(std::size_t N, std::size_t nev, std::size_t nex, T* H, std::size_t ldh, T* V1, std::size_t ldv,
+             R* ritzv)
+        : N_(N), nev_(nev), nex_(nex), nevex_(nev + nex), H_(H), ldh_(ldh), V_(V1), ldv_(ldv), ritzv_(ritzv),
+          config_(N, nev, nex)
+    {
+        if (N == 0 || nevex_ == 0 || nevex_ > N)
+            throw std::invalid_argument("ChASEGPU: need 0 < nev+nex <= N");
+        if (ldh < N || ldv < N)
+            throw std::invalid_argument("ChASEGPU: leading dimension smaller than N");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw std::runtime_error("ChASEGPU: no CUDA device available (this backend has no CPU fallback)");
+        CB2_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        ld_ = roundup(N_, 16);
+        ldg_ = roundup(nevex_, 16);
+        dH_ = alloc<T>(ld_ * N_);
+        dV1_ = alloc<T>(ld_ * nevex_);
+        dV2_ = alloc<T>(ld_ * nevex_);
+        dW_ = alloc<T>(ld_ * nevex_);
+        dG_ = alloc<T>(ldg_ * nevex_);
+        dZ_ = alloc<T>(ldg_ * nevex_);
+        heev_ws_bytes_ = chase_b200_heev_ws_bytes((int64_t)nevex_, kCplx ? 1 : 0);
+        heev_ws_ = alloc<unsigned char>(heev_ws_bytes_);
+        trsm_ws_bytes_ = chase_b200_trsm_ws_bytes((int64_t)nevex_, (int)sizeof(T));
+        trsm_ws_ = alloc<unsigned char>(trsm_ws_bytes_);
+        splitk_ws_bytes_ = std::max<std::size_t>(std::size_t(64) << 20, 4 * nevex_ * nevex_ * 16);
+        splitk_ws_ = alloc<unsigned char>(splitk_ws_bytes_);
+        dTheta_ = alloc<double>(nevex_);
+        dNorms_ = alloc<double>(nevex_);
+        dInfo_ = alloc<int>(4);
+        dIdx_ = alloc<int>(2 * nevex_);
+        resid_.assign(nevex_, R(0));
+        perm_.resize(nevex_);
+        for (std::size_t i = 0; i < nevex_; ++i)
+            perm_[i] = (int)i;
+        const char* e = std::getenv("CHASE_B200_DEVICE_RNG");
+        device_rng_ = e && std::atoi(e) != 0;
+    }
+    ChASEGPU(const ChASEGPU&) = delete;
+    ~ChASEGPU() override
+    {
+        for (void* p : allocs_)
+            cudaFree(p);
+        if (stream_)
+            cudaStreamDestroy(stream_);
+    }
+
+    // ---- ChaseBase ----------------------------------------------------------
+    void Start() override { locked_ = 0; }
+
+    void initVecs(bool random) override
+    {
+        if (random && device_rng_)
+        {
+            CB2_KCHECK(KK::rng_normal((int64_t)N_, (int64_t)nevex_, dV1_, (int64_t)ld_, 24141ull, stream_));
+        }
+        else
+        {
+            if (random)
+            {
+                fill_start_vectors<T>(N_, nevex_, V_, ldv_);
+            }
+            CB2_CHECK(cudaMemcpy2DAsync(dV1_, ld_ * sizeof(T), V_, ldv_ * sizeof(T), N_ * sizeof(T), nevex_,
+                                        cudaMemcpyHostToDevice, stream_));
+        }
+        CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nevex_, dV1_, (int64_t)ld_, dV2_, (int64_t)ld_, stream_));
+        // the host matrix is (re-)read at every solve: callers fill or perturb H
+        // after construction (examples/4_interface/4_c_serial_chase.c:49-66)
+        CB2_CHECK(cudaMemcpy2DAsync(dH_, ld_ * sizeof(T), H_, ldh_ * sizeof(T), N_ * sizeof(T), N_,
+                                    cudaMemcpyHostToDevice, stream_));
+        reset_perm();
+        shift_ = 0.0;
+    }
+
+    void Shift(T c, bool /*isunshift*/ = false) override { shift_ += (double)std::real(c); }
+
+    void HEMM(std::size_t block, T alpha, T beta, std::size_t offset_left, std::size_t offset_right = 0) override
+    {
+        flush_perm();
+        const std::size_t ncols = (offset_right < block) ? block - offset_right : 0;
+        if (ncols > 0)
+        {
+            const std::size_t c0 = offset_left + locked_;
+            // A_eff = A + shift_ I  ->  alpha (A - (-shift_) I) B + beta C
+            CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)ncols, b200::re_of(alpha), b200::im_of(alpha), dH_, (int64_t)ld_,
+                                dV1_ + c0 * ld_, (int64_t)ld_, b200::re_of(beta), b200::im_of(beta), dV2_ + c0 * ld_,
+                                (int64_t)ld_, -shift_, nullptr, stream_));
+            hemm_cols_ += ncols;
+        }
+        std::swap(dV1_, dV2_);
+    }
+
+    void HEMM_H2(std::size_t, T, T, T, std::size_t, std::size_t = 0) override
+    {
+        throw std::runtime_error("chase_b200: pseudo-Hermitian HEMM_H2 is not implemented yet");
+    }
+    void ApplyKconjugate(std::size_t) override
+    {
+        throw std::runtime_error("chase_b200: pseudo-Hermitian ApplyKconjugate is not implemented yet");
+    }
+
+    void QR(std::size_t /*fixednev*/, R cond) override
+    {
+        flush_perm();
+        // keep the locked vectors: CholQR runs on all nev+nex columns
+        CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)locked_, dV1_, (int64_t)ld_, dV2_, (int64_t)ld_, stream_));
+
+        int disable = config_.DoCholQR() ? 0 : 1;
+        if (const char* s = std::getenv("CHASE_DISABLE_CHOLQR"))
+            disable = std::atoi(s);
+        R thr_upper = (sizeof(R) == 8) ? R(1e8) : R(1e4);
+        R thr_lower = (sizeof(R) == 8) ? R(2e1) : R(1e1);
+        if (const char* s = std::getenv("CHASE_CHOLQR1_THLD"))
+            thr_lower = (R)std::atof(s);
+
+        int info = 1;
+        if (disable == 1 && cond != R(1.0))
+        {
+            // The reference switches to Householder QR here.  Until the Householder
+            // kernel lands this backend uses its most robust Cholesky variant.
+            info = shifted_cholqr2(1.0);
+            last_qr_ = "shifted2(no-cholqr requested)";
+        }
+        else if (cond > thr_upper)
+        {
+            info = shifted_cholqr2(1.0);
+            last_qr_ = "shifted2";
+        }
+        else if (cond < thr_lower)
+        {
+            info = chol_round(false, 0.0);
+            last_qr_ = "chol1";
+        }
+        else
+        {
+            info = chol_round(false, 0.0);
+            if (info == 0)
+                info = chol_round(false, 0.0);
+            last_qr_ = "chol2";
+        }
+        if (info != 0)
+        {
+            // reference: Householder fallback (chase_gpu.hpp:889-919).  Here: shifted
+            // CholQR with a growing shift, then fail loudly.
+            double boost = 1.0;
+            for (int attempt = 0; attempt < 4 && info != 0; ++attempt, boost *= 100.0)
+                info = shifted_cholqr2(boost);
+            last_qr_ += "+shifted-fallback";
+            if (info != 0)
+                throw std::runtime_error("chase_b200: CholQR failed (potrf info=" + std::to_string(info) +
+                                         ") and no Householder fallback is available yet");
+        }
+        qr_log_.push_back(last_qr_);
+        CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)locked_, dV2_, (int64_t)ld_, dV1_, (int64_t)ld_, stream_));
+    }
+
+    void RR(R* ritzv, std::size_t block) override
+    {
+        flush_perm();
+        if (block == 0)
+            return;
+        T* Q = dV1_ + locked_ * ld_;
+        T* W = dV2_ + locked_ * ld_;
+        // W = A Q   (the reference forms A^H Q; A is Hermitian)
+        CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)block, 1.0, 0.0, dH_, (int64_t)ld_, Q, (int64_t)ld_, 0.0, 0.0, W,
+                            (int64_t)ld_, 0.0, nullptr, stream_));
+        // G = W^H Q
+        CB2_KCHECK(KK::gemm(1, 0, (int64_t)block, (int64_t)block, (int64_t)N_, 1.0, 0.0, W, (int64_t)ld_, Q,
+                            (int64_t)ld_, 0.0, 0.0, dG_, (int64_t)ldg_, 0, splitk_ws_, splitk_ws_bytes_, stream_));
+        std::vector<double> w(block);
+        int sweeps = 0;
+        int rc = KK::heev((int64_t)block, dG_, (int64_t)ldg_, dZ_, (int64_t)ldg_, w.data(), heev_ws_, heev_ws_bytes_,
+                          &sweeps, stream_);
+        if (rc != 0)
+            throw std::runtime_error("chase_b200: Hermitian eigensolver failed in RR (rc=" + std::to_string(rc) + ")");
+        heev_sweeps_ += sweeps;
+        for (std::size_t i = 0; i < block; ++i)
+            ritzv[i] = (R)w[i];
+        // V2 = Q Z ; swap
+        CB2_KCHECK(KK::gemm(0, 0, (int64_t)N_, (int64_t)block, (int64_t)block, 1.0, 0.0, Q, (int64_t)ld_, dZ_,
+                            (int64_t)ldg_, 0.0, 0.0, W, (int64_t)ld_, 0, nullptr, 0, stream_));
+        std::swap(dV1_, dV2_);
+    }
+
+    void Sort(R*, R*, R*) override {}
+
+    void Resd(R* ritzv, R* resd, std::size_t /*fixednev*/) override
+    {
+        flush_perm();
+        const std::size_t k = nevex_ - locked_;
+        if (k == 0)
+            return;
+        std::vector<double> th(k);
+        for (std::size_t i = 0; i < k; ++i)
+            th[i] = (double)ritzv[i];
+        CB2_CHECK(cudaMemcpyAsync(dTheta_, th.data(), k * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        T* V = dV1_ + locked_ * ld_;
+        T* W = dV2_ + locked_ * ld_;
+        // W = A V - V diag(theta)
+        CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)k, 1.0, 0.0, dH_, (int64_t)ld_, V, (int64_t)ld_, 0.0, 0.0, W,
+                            (int64_t)ld_, 0.0, dTheta_, stream_));
+        CB2_KCHECK(KK::colnorms((int64_t)N_, (int64_t)k, W, (int64_t)ld_, dNorms_, 1, stream_));
+        std::vector<double> nr(k);
+        CB2_CHECK(cudaMemcpyAsync(nr.data(), dNorms_, k * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        for (std::size_t i = 0; i < k; ++i)
+            resd[i] = (R)nr[i];
+    }
+
+    void Lanczos(std::size_t M, R* upperb) override
+    {
+        lanczosIter_ = M;
+        numLanczos_ = 1;
+        std::vector<R> theta(M), tau(M), rv(M * M);
+        run_lanczos(M, 1, upperb, theta.data(), tau.data(), rv.data(), false);
+    }
+
+    void Lanczos(std::size_t M, std::size_t numvec, R* upperb, R* ritzv, R* Tau, R* ritzV) override
+    {
+        lanczosIter_ = M;
+        numLanczos_ = numvec;
+        run_lanczos(M, numvec, upperb, ritzv, Tau, ritzV, true);
+    }
+
+    void LanczosDos(std::size_t idx, std::size_t m, T* ritzVc) override
+    {
+        flush_perm();
+        CB2_CHECK(cudaMemcpy2DAsync(dZ_, ldg_ * sizeof(T), ritzVc, m * sizeof(T), m * sizeof(T), idx,
+                                    cudaMemcpyHostToDevice, stream_));
+        CB2_KCHECK(KK::gemm(0, 0, (int64_t)N_, (int64_t)idx, (int64_t)m, 1.0, 0.0, dV1_, (int64_t)ld_, dZ_,
+                            (int64_t)ldg_, 0.0, 0.0, dV2_, (int64_t)ld_, 0, nullptr, 0, stream_));
+        CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)m, dV2_, (int64_t)ld_, dV1_, (int64_t)ld_, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_)); // ritzVc is caller-owned
+    }
+
+    void Swap(std::size_t i, std::size_t j) override
+    {
+        std::swap(perm_[i], perm_[j]);
+        perm_dirty_ = true;
+        swaps_++;
+    }
+
+    void Lock(std::size_t new_converged) override { locked_ += new_converged; }
+
+    bool checkSymmetryEasy() override
+    {
+        CB2_CHECK(cudaMemcpy2DAsync(dH_, ld_ * sizeof(T), H_, ldh_ * sizeof(T), N_ * sizeof(T), N_,
+                                    cudaMemcpyHostToDevice, stream_));
+        unsigned long long* bad = reinterpret_cast<unsigned long long*>(dNorms_);
+        CB2_CHECK(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), stream_));
+        const double tol = (sizeof(R) == 8) ? 1e-10 : 1e-5;
+        CB2_KCHECK(KK::herm_check((int64_t)N_, dH_, (int64_t)ld_, tol, bad, stream_));
+        unsigned long long h = 0;
+        CB2_CHECK(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        is_sym_ = (h == 0);
+        return is_sym_;
+    }
+    bool isSym() override { return true; }
+    bool checkPseudoHermicityEasy() override { return false; }
+    bool isPseudoHerm() override { return false; }
+    void symOrHermMatrix(char uplo) override
+    {
+        // acts on the caller's host matrix (re-uploaded at the next initVecs), like the reference
+        for (std::size_t j = 0; j < N_; ++j)
+            for (std::size_t i = j + 1; i < N_; ++i)
+            {
+                if (uplo == 'U')
+                    H_[i + j * ldh_] = conjugate(H_[j + i * ldh_]);
+                else
+                    H_[j + i * ldh_] = conjugate(H_[i + j * ldh_]);
+            }
+    }
+
+    void End() override
+    {
+        flush_perm();
+        CB2_CHECK(cudaMemcpy2DAsync(V_, ldv_ * sizeof(T), dV1_, ld_ * sizeof(T), N_ * sizeof(T), nevex_,
+                                    cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+    }
+
+    std::size_t GetN() const override { return N_; }
+    std::size_t GetNev() override { return nev_; }
+    std::size_t GetNex() override { return nex_; }
+    std::size_t GetLanczosIter() override { return lanczosIter_; }
+    std::size_t GetNumLanczos() override { return numLanczos_; }
+    std::size_t GetRitzvBlockSize() const override { return nevex_; }
+    R* GetRitzv() override { return ritzv_; }
+    R* GetResid() override { return resid_.data(); }
+    ChaseConfig<T>& GetConfig() override { return config_; }
+    int get_nprocs() override { return 1; }
+    int get_rank() override { return 0; }
+    void Output(LogLevel, std::string s, const char* = "algorithm") override
+    {
+        if (std::getenv("CHASE_B200_VERBOSE"))
+            std::cout << s;
+    }
+
+    // ---- extras (not part of ChaseBase) ------------------------------------
+    const std::vector<std::string>& qr_log() const { return qr_log_; }
+    void clear_logs()
+    {
+        qr_log_.clear();
+        heev_sweeps_ = 0;
+        hemm_cols_ = 0;
+        swaps_ = 0;
+        gathers_ = 0;
+    }
+    std::size_t heev_sweeps() const { return heev_sweeps_; }
+    std::size_t gather_passes() const { return gathers_; }
+    cudaStream_t stream() const { return stream_; }
+    T* device_H() { return dH_; }
+    T* device_V1() { return dV1_; }
+    std::size_t device_ld() const { return ld_; }
+    void set_host_buffers(T* H, std::size_t ldh, T* V, std::size_t ldv, R* ritzv)
+    {
+        H_ = H;
+        ldh_ = ldh;
+        V_ = V;
+        ldv_ = ldv;
+        ritzv_ = ritzv;
+    }
+
+private:
+    static std::size_t roundup(std::size_t a, std::size_t b) { return (a + b - 1) / b * b; }
+    template <class U>
+    U* alloc(std::size_t n)
+    {
+        void* p = nullptr;
+        CB2_CHECK(cudaMalloc(&p, std::max<std::size_t>(n, 1) * sizeof(U)));
+        CB2_CHECK(cudaMemset(p, 0, std::max<std::size_t>(n, 1) * sizeof(U)));
+        allocs_.push_back(p);
+        return static_cast<U*>(p);
+    }
+    void reset_perm()
+    {
+        for (std::size_t i = 0; i < nevex_; ++i)
+            perm_[i] = (int)i;
+        perm_dirty_ = false;
+    }
+    // apply all pending Swap()s: V1[:, j] <- V1_old[:, perm_[j]]
+    void flush_perm()
+    {
+        if (!perm_dirty_)
+            return;
+        std::vector<int> idx;
+        std::vector<int> src, dst;
+        for (std::size_t j = 0; j < nevex_; ++j)
+            if (perm_[j] != (int)j)
+            {
+                src.push_back(perm_[j]);
+                dst.push_back((int)j);
+            }
+        const int cnt = (int)dst.size();
+        if (cnt > 0)
+        {
+            idx = src;
+            idx.insert(idx.end(), dst.begin(), dst.end());
+            CB2_CHECK(cudaMemcpyAsync(dIdx_, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+            CB2_KCHECK(KK::gather_cols((int64_t)N_, cnt, dIdx_, dIdx_ + cnt, dV1_, (int64_t)ld_, dW_, (int64_t)ld_,
+                                       stream_));
+            CB2_KCHECK(KK::gather_cols((int64_t)N_, cnt, dIdx_ + cnt, dIdx_ + cnt, dW_, (int64_t)ld_, dV1_,
+                                       (int64_t)ld_, stream_));
+            CB2_CHECK(cudaStreamSynchronize(stream_)); // idx is a host temporary
+            gathers_++;
+        }
+        reset_perm();
+    }
+
+    // one CholQR round on all nev+nex columns; shift_boost > 0 adds the shifted-CholQR shift
+    int chol_round(bool shifted, double shift_boost)
+    {
+        const int64_t n = (int64_t)nevex_;
+        CB2_KCHECK(KK::gemm(1, 0, n, n, (int64_t)N_, 1.0, 0.0, dV1_, (int64_t)ld_, dV1_, (int64_t)ld_, 0.0, 0.0, dG_,
+                            (int64_t)ldg_, 1, splitk_ws_, splitk_ws_bytes_, stream_));
+        if (shifted)
+        {
+            // reference CPU formula (cpu/cholqr1.hpp:153-166): sqrt(rows) * eps (double) / 10 * eps (float)
+            const double scale = (sizeof(R) == 8) ? std::sqrt((double)N_) * 2.220446049250313e-16
+                                                  : 10.0 * 1.1920928955078125e-07;
+            CB2_KCHECK(KK::shift_abstrace(n, dG_, (int64_t)ldg_, scale * shift_boost, nullptr, stream_));
+        }
+        CB2_CHECK(cudaMemsetAsync(dInfo_, 0, sizeof(int), stream_));
+        CB2_KCHECK(KK::potrf(n, dG_, (int64_t)ldg_, dInfo_, stream_));
+        int info = 0;
+        CB2_CHECK(cudaMemcpyAsync(&info, dInfo_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        if (info != 0)
+            return info;
+        CB2_KCHECK(KK::trsm((int64_t)N_, n, dG_, (int64_t)ldg_, dV1_, (int64_t)ld_, dW_, (int64_t)ld_, trsm_ws_,
+                            trsm_ws_bytes_, stream_));
+        std::swap(dV1_, dW_);
+        return 0;
+    }
+    int shifted_cholqr2(double boost)
+    {
+        int info = chol_round(true, boost);
+        if (info)
+            return info;
+        info = chol_round(false, 0.0);
+        if (info)
+            return info;
+        return chol_round(false, 0.0);
+    }
+
+    void run_lanczos(std::size_t M, std::size_t numvec, R* upperb, R* Theta, R* Tau, R* ritzV, bool multi)
+    {
+        flush_perm();
+        if (M > 48)
+            throw std::runtime_error("chase_b200: Lanczos with more than 48 steps is not supported yet");
+        const int nv = (int)numvec, m = (int)M;
+        if (lan_nv_ < numvec)
+        {
+            lan_v_ = alloc<T>(3 * ld_ * numvec);
+            lan_nv_ = numvec;
+        }
+        if (lan_m_ < M * numvec)
+        {
+            lan_d_ = alloc<double>(M * numvec);
+            lan_e_ = alloc<double>(M * numvec);
+            lan_w_ = alloc<double>(M * numvec);
+            lan_Z_ = alloc<double>(M * M * numvec);
+            lan_rb_ = alloc<double>(numvec + 1);
+            lan_m_ = M * numvec;
+        }
+        T* v0 = lan_v_;
+        T* v1 = lan_v_ + ld_ * numvec;
+        T* v2 = lan_v_ + 2 * ld_ * numvec;
+        CB2_CHECK(cudaMemsetAsync(lan_d_, 0, M * numvec * sizeof(double), stream_));
+        CB2_CHECK(cudaMemsetAsync(lan_e_, 0, M * numvec * sizeof(double), stream_));
+        CB2_KCHECK(KK::lacpy((int64_t)N_, nv, dV1_, (int64_t)ld_, v1, (int64_t)ld_, stream_));
+        CB2_KCHECK(KK::normalize_cols((int64_t)N_, nv, v1, (int64_t)ld_, stream_));
+        for (int k = 0; k < m; ++k)
+        {
+            if (multi) // V1[:, k] <- current vector of the LAST run (cpu/lanczos.hpp:85-88)
+                CB2_KCHECK(KK::lacpy((int64_t)N_, 1, v1 + (std::size_t)(nv - 1) * ld_, (int64_t)ld_, dV1_ + (std::size_t)k * ld_,
+                                     (int64_t)ld_, stream_));
+            CB2_KCHECK(KK::gemv_conjt((int64_t)N_, (int64_t)N_, dH_, (int64_t)ld_, v1, (int64_t)ld_, nv, v2,
+                                      (int64_t)ld_, stream_));
+            CB2_KCHECK(KK::lanczos_step((int64_t)N_, nv, k, m, v0, v1, v2, (int64_t)ld_, lan_d_, lan_e_, lan_rb_,
+                                        stream_));
+            if (k == m - 1)
+                break;
+            T* t = v0;
+            v0 = v1;
+            v1 = v2;
+            v2 = t;
+        }
+        if (multi)
+            CB2_KCHECK(KK::lacpy((int64_t)N_, nv, v1, (int64_t)ld_, dV1_, (int64_t)ld_, stream_));
+        CB2_KCHECK(chase_b200_tridiag_eig(m, nv, lan_d_, lan_e_, m, lan_w_, lan_Z_, stream_));
+        std::vector<double> w(M * numvec), Z(M * M * numvec), rb(numvec);
+        CB2_CHECK(cudaMemcpyAsync(w.data(), lan_w_, w.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaMemcpyAsync(Z.data(), lan_Z_, Z.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaMemcpyAsync(rb.data(), lan_rb_, rb.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        for (std::size_t i = 0; i < numvec; ++i)
+        {
+            for (std::size_t k = 0; k < M; ++k)
+            {
+                Theta[k + M * i] = (R)w[i * M + k];
+                const R z0 = (R)Z[i * M * M + 0 + k * M];
+                Tau[k + i * M] = std::abs(z0) * std::abs(z0);
+            }
+        }
+        for (std::size_t q = 0; q < M * M; ++q)
+            ritzV[q] = (R)Z[(numvec - 1) * M * M + q];
+        R ub = std::max(std::abs(Theta[0]), std::abs(Theta[M - 1])) + std::abs((R)rb[0]);
+        for (std::size_t i = 1; i < numvec; ++i)
+        {
+            const R mx = std::max(std::abs(Theta[i * M]), std::abs(Theta[(i + 1) * M - 1])) + std::abs((R)rb[i]);
+            ub = std::max(mx, ub);
+        }
+        *upperb = ub;
+    }
+
+    std::size_t N_, nev_, nex_, nevex_;
+    T* H_;
+    std::size_t ldh_;
+    T* V_;
+    std::size_t ldv_;
+    R* ritzv_;
+    ChaseConfig<T> config_;
+    cudaStream_t stream_ = nullptr;
+    std::size_t ld_ = 0, ldg_ = 0;
+    T *dH_ = nullptr, *dV1_ = nullptr, *dV2_ = nullptr, *dW_ = nullptr, *dG_ = nullptr, *dZ_ = nullptr;
+    unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr;
+    std::size_t heev_ws_bytes_ = 0, trsm_ws_bytes_ = 0, splitk_ws_bytes_ = 0;
+    double *dTheta_ = nullptr, *dNorms_ = nullptr;
+    int *dInfo_ = nullptr, *dIdx_ = nullptr;
+    T* lan_v_ = nullptr;
+    double *lan_d_ = nullptr, *lan_e_ = nullptr, *lan_w_ = nullptr, *lan_Z_ = nullptr, *lan_rb_ = nullptr;
+    std::size_t lan_nv_ = 0, lan_m_ = 0;
+    std::vector<void*> allocs_;
+    std::vector<R> resid_;
+    std::vector<int> perm_;
+    bool perm_dirty_ = false;
+    std::size_t locked_ = 0;
+    double shift_ = 0.0;
+    std::size_t lanczosIter_ = 0, numLanczos_ = 0;
+    bool device_rng_ = false, is_sym_ = true;
+    std::string last_qr_;
+    std::vector<std::string> qr_log_;
+    std::size_t heev_sweeps_ = 0, hemm_cols_ = 0, swaps_ = 0, gathers_ = 0;
+};
+
+} // namespace Impl
+} // namespace chase

@@ -1,0 +1,120 @@
+/* chase_b200 — kernel-level C ABI (device pointers in, status out).
+ *
+ * This is the thin layer the C++ host orchestration (chase_b200/host) calls;
+ * every entry point is a hand-written sm_100a CUDA kernel launcher and stands
+ * in for one vendor-library call (or helper kernel) of the reference's GPU
+ * backends.  No cuBLAS / cuSOLVER / cuRAND is linked.
+ *
+ * Conventions
+ *   - one function per ChASE value type, suffix _s/_d/_c/_z
+ *     (float, double, complex<float>, complex<double>; complex = interleaved
+ *     re,im exactly like std::complex / the reference);
+ *   - all matrices column-major with an explicit leading dimension (elements);
+ *   - complex scalars cross the ABI as (re, im) doubles;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - no allocation inside: workspaces are passed in;
+ *   - return 0 = ok, <0 = CUDA / argument error (message on stderr),
+ *     >0 = numerical info where stated (LAPACK convention).
+ */
+#ifndef CHASE_B200_KERNELS_H
+#define CHASE_B200_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define CHASE_B200_KERNEL_API(X)                                                                                       \
+    /* C <- alpha op(A) op(B) + beta C; ta/tb: 0 = N, 1 = conjugate transpose; uplo: 0 all, 1 upper tiles only,       \
+       2 lower tiles only. Replaces cublasTgemm / cublasTsyherk                                                        \
+       (reference linalg/internal/cuda/rayleighRitz.hpp:125-214, cuda/cholqr.hpp:110-117). */                         \
+    int chase_b200_gemm_##X(int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha_re, double alpha_im,        \
+                            const void* A, int64_t lda, const void* B, int64_t ldb, double beta_re, double beta_im,   \
+                            void* C, int64_t ldc, int uplo, void* ws, size_t ws_bytes, void* stream);                 \
+    /* Filter step: C <- alpha (A - shift I) B + beta C on an n x k panel (A is n x n Hermitian and is NOT            \
+       modified).  If theta != NULL (device, k doubles) the shift is per column: C <- alpha (A B - B diag(theta))     \
+       + beta C, which with alpha=1, beta=0 is the residual block A V - V Theta.                                      \
+       Replaces Shift + cublasTgemm in ChASEGPU::HEMM (reference Impl/chase_gpu/chase_gpu.hpp:599-603, 656-678)       \
+       and the GEMM of cuda::residuals (linalg/internal/cuda/residuals.hpp:92-110). */                                \
+    int chase_b200_hemm_##X(int64_t n, int64_t k, double alpha_re, double alpha_im, const void* A, int64_t lda,       \
+                            const void* B, int64_t ldb, double beta_re, double beta_im, void* C, int64_t ldc,         \
+                            double shift, const double* theta, void* stream);                                         \
+    /* Upper Cholesky G = R^H R in place (strict lower part untouched). *info_dev (device int, must be zeroed by      \
+       the caller) receives the 1-based index of the first non-positive pivot, LAPACK ?potrf convention.              \
+       Replaces cusolverDnTpotrf (reference cuda/cholqr.hpp:119-125). */                                              \
+    int chase_b200_potrf_##X(int64_t n, void* G, int64_t ldg, int* info_dev, void* stream);                           \
+    /* X <- V R^-1 with R upper triangular n x n (V is overwritten with intermediates).  ws: at least                 \
+       chase_b200_trsm_ws_bytes(n) bytes.  Replaces cublasTtrsm(RIGHT, UPPER, N) (reference cuda/cholqr.hpp:127-132) \
+     */                                                                                                                \
+    int chase_b200_trsm_##X(int64_t rows, int64_t n, const void* R, int64_t ldr, void* V, int64_t ldv, void* Xout,    \
+                            int64_t ldx, void* ws, size_t ws_bytes, void* stream);                                    \
+    /* G_ii += scale * sum_i |G_ii| ; the shift is also stored to *shift_out_dev (device double, may be NULL).        \
+       Replaces absTrace + shiftDiagonalFromDeviceShift (reference cuda/cholqr.hpp:391-420). */                       \
+    int chase_b200_shift_abstrace_##X(int64_t n, void* G, int64_t ldg, double scale, double* shift_out_dev,           \
+                                      void* stream);                                                                   \
+    /* Hermitian eigen-decomposition of the n x n matrix G (LOWER triangle referenced): eigenvalues ascending to      \
+       w_host (host, n doubles), eigenvectors to Z (device).  Synchronises the stream.  ws: at least                   \
+       chase_b200_heev_ws_bytes(n, is_complex).  *sweeps (host, may be NULL) gets the Jacobi sweep count.             \
+       Returns >0 if not converged.  Replaces cusolverDnTheevd (reference cuda/rayleighRitz.hpp:169-209). */          \
+    int chase_b200_heev_##X(int64_t n, const void* G, int64_t ldg, void* Z, int64_t ldz, double* w_host, void* ws,    \
+                            size_t ws_bytes, int* sweeps, void* stream);                                              \
+    /* out[j] = ||X[:, j]||_2 (take_sqrt != 0) or its square.  Replaces residual_gpu's reduction                      \
+       (reference linalg/internal/cuda/residuals.cu:113-296). */                                                      \
+    int chase_b200_colnorms_##X(int64_t rows, int64_t cols, const void* Xm, int64_t ldx, double* out_dev,             \
+                                int take_sqrt, void* stream);                                                         \
+    /* dst <- src (rows x cols).  Replaces cuda::t_lacpy('A') (reference cuda/lacpy.cu:62-496). */                    \
+    int chase_b200_lacpy_##X(int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst, int64_t ldd,        \
+                             void* stream);                                                                            \
+    /* dst[:, dcols[t]] <- src[:, scols[t]], t < cnt (index arrays on the device; src != dst).  Batched form of       \
+       the reference's per-call cublasTswap (Impl/chase_gpu/chase_gpu.hpp:1000-1006). */                              \
+    int chase_b200_gather_cols_##X(int64_t rows, int cnt, const int* scols_dev, const int* dcols_dev,                 \
+                                   const void* src, int64_t lds, void* dst, int64_t ldd, void* stream);               \
+    /* Y[:, v] <- A^H X[:, v], v < nv (A is rows x cols).  HBM-bound Lanczos product; replaces the 4-column           \
+       cublasTgemm(OP_C) of cuda::lanczos (reference linalg/internal/cuda/lanczos.hpp:178-186). */                    \
+    int chase_b200_gemv_conjt_##X(int64_t rows, int64_t cols, const void* A, int64_t lda, const void* Xm,             \
+                                  int64_t ldx, int nv, void* Y, int64_t ldy, void* stream);                           \
+    /* One fused Lanczos step for nv vectors (dot, two axpys, norm, scale; scalars stay on the device).               \
+       Replaces the batched dot/axpy/norm kernels of reference cuda/lanczos_kernels.cu. */                             \
+    int chase_b200_lanczos_step_##X(int64_t rows, int nv, int k, int M, const void* v0, const void* v1, void* v2,     \
+                                    int64_t ld, double* d_dev, double* e_dev, double* rbeta_dev, void* stream);       \
+    /* X[:, j] /= ||X[:, j]||  (reference cuda/lanczos.hpp:112-131) */                                                \
+    int chase_b200_normalize_cols_##X(int64_t rows, int64_t cols, void* Xm, int64_t ldx, void* stream);               \
+    /* Philox4x32-10 + Box-Muller N(0,1) fill (production-mode start vectors; reference                               \
+       cuda/random_normal_distribution.cu:21-93 uses cuRAND Philox). */                                               \
+    int chase_b200_rng_normal_##X(int64_t rows, int64_t cols, void* Xm, int64_t ldx, uint64_t seed, void* stream);    \
+    /* *bad_dev (device, zeroed by caller) += #entries of the lower triangle with |A_ij - conj(A_ji)| >               \
+       tol (|A_ij| + |A_ji|).  Replaces checkSymmetryEasy (reference chase_gpu.hpp:463-470). */                       \
+    int chase_b200_herm_check_##X(int64_t n, const void* A, int64_t lda, double tol, unsigned long long* bad_dev,     \
+                                  void* stream);                                                                       \
+    /* A_ii += c (real part).  Replaces chase_shift_matrix (reference cuda/shiftDiagonal.cu:23-50). */                \
+    int chase_b200_shift_diag_##X(int64_t n, void* A, int64_t lda, double c, void* stream);                           \
+    /* Mirror one triangle onto the other (symOrHermMatrix, reference chase_gpu.hpp:472-505). */                      \
+    int chase_b200_herm_mirror_##X(int64_t n, void* A, int64_t lda, int from_upper, void* stream);
+
+    CHASE_B200_KERNEL_API(s)
+    CHASE_B200_KERNEL_API(d)
+    CHASE_B200_KERNEL_API(c)
+    CHASE_B200_KERNEL_API(z)
+
+    /* Batched symmetric tridiagonal eigen-solve (n <= 48) fully on the device: matrix b has diagonal
+       d[b*ldde + 0..n-1] and off-diagonal e[b*ldde + 0..n-2]; w[b*n + i] ascending, Z[b*n*n + i + j*n].
+       Replaces the host LAPACK ?stemr of the reference (linalg/internal/cuda/lanczos.hpp:270-299). */
+    int chase_b200_tridiag_eig(int n, int batch, const double* d_dev, const double* e_dev, int ldde, double* w_dev,
+                               double* Z_dev, void* stream);
+
+    size_t chase_b200_trsm_ws_bytes(int64_t n, int elem_bytes);
+    size_t chase_b200_heev_ws_bytes(int64_t n, int is_complex);
+    /* Which HEMM implementation handles this shape: 0 = generic DMMA tiles, 1 = TMA-fed DMMA pipeline. */
+    int chase_b200_hemm_path(int dtype_code, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc);
+    /* FP64 tensor-pipe microbenchmark: runs `iters` register-resident DMMA.8x8x4 per warp on every SM and
+       returns the achieved FLOP/s (the roofline denominator for the filter; MEASURED_PEAKS.json has no FP64). */
+    double chase_b200_dmma_peak(int iters, void* stream);
+    const char* chase_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,117 @@
+/* chase_b200 — the reference-compatible C / Fortran-callable interface of the
+ * sequential (single-GPU) solver.  Names, argument order, by-pointer Fortran
+ * convention and trailing underscore are those of the reference's
+ * interface/chase_c_interface.h:17-41,177-180,217-239, so a C or Fortran
+ * application linked against the reference's libchase_c (GPU build) can link
+ * against libchase_b200.so instead.
+ *
+ *   ?chase_init_(N, nev, nex, H, ldh, V, ritzv, init)   reference :17-24
+ *       constructs the process-global solver for that scalar type; the caller
+ *       owns H (column-major, ldh >= N; read at every solve), V (N x (nev+nex),
+ *       ld = N) and ritzv (nev+nex); V / ritzv may be NULL (then allocated
+ *       internally, fetch results with ?chase_get_eigenpairs_).  *init = 1.
+ *   ?chase_init_internal_(N, nev, nex, H, ldh, init)     reference :25-33
+ *   ?chase_(deg, tol, mode, opt, qr)                     reference :38-41
+ *       mode 'R' random / 'A' approximate start vectors; opt 'S' optimise
+ *       degrees / 'N'; qr 'C' CholeskyQR / 'H' Householder.
+ *   ?chase_finalize_(flag)                               reference :34-37
+ *   ?chase_get_eigenpairs_(V, ld, ritzv)                 reference :177-180
+ *   chase_set_*_ / chase_has_*_ / chase_get_version_     reference :217-239
+ *
+ * Not re-entrant and not thread-safe (one process-global solver per type), as
+ * in the reference (interface/chase_c_interface.cpp:71-97).
+ */
+#ifndef CHASE_B200_C_INTERFACE_H
+#define CHASE_B200_C_INTERFACE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#define CHASE_B200_CF float
+#define CHASE_B200_CD double
+#else
+#define CHASE_B200_CF float _Complex
+#define CHASE_B200_CD double _Complex
+#endif
+
+    void dchase_init_(int* N, int* nev, int* nex, double* H, int* ldh, double* V, double* ritzv, int* init);
+    void schase_init_(int* N, int* nev, int* nex, float* H, int* ldh, float* V, float* ritzv, int* init);
+    void cchase_init_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, CHASE_B200_CF* V, float* ritzv,
+                      int* init);
+    void zchase_init_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, CHASE_B200_CD* V, double* ritzv,
+                      int* init);
+    void dchase_init_internal_(int* N, int* nev, int* nex, double* H, int* ldh, int* init);
+    void schase_init_internal_(int* N, int* nev, int* nex, float* H, int* ldh, int* init);
+    void cchase_init_internal_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, int* init);
+    void zchase_init_internal_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, int* init);
+
+    void dchase_finalize_(int* flag);
+    void schase_finalize_(int* flag);
+    void cchase_finalize_(int* flag);
+    void zchase_finalize_(int* flag);
+
+    void dchase_(int* deg, double* tol, char* mode, char* opt, char* qr);
+    void schase_(int* deg, float* tol, char* mode, char* opt, char* qr);
+    void zchase_(int* deg, double* tol, char* mode, char* opt, char* qr);
+    void cchase_(int* deg, float* tol, char* mode, char* opt, char* qr);
+
+    void dchase_get_eigenpairs_(double* LEigsV, int* ld, double* ritzv);
+    void schase_get_eigenpairs_(float* LEigsV, int* ld, float* ritzv);
+    void cchase_get_eigenpairs_(CHASE_B200_CF* LEigsV, int* ld, float* ritzv);
+    void zchase_get_eigenpairs_(CHASE_B200_CD* LEigsV, int* ld, double* ritzv);
+
+    /* unified configuration setters: act on the first initialised solver in the order d, s, z, c */
+    void chase_set_tol_(double* tol);
+    void chase_set_deg_(int* deg);
+    void chase_set_max_deg_(int* max_deg);
+    void chase_set_deg_extra_(int* deg_extra);
+    void chase_set_max_iter_(int* max_iter);
+    void chase_set_lanczos_iter_(int* lanczos_iter);
+    void chase_set_num_lanczos_(int* num_lanczos);
+    void chase_set_approx_(int* flag);
+    void chase_set_opt_(int* flag);
+    void chase_set_cholqr_(int* flag);
+    void chase_enable_sym_check_(int* flag);
+    void chase_set_decaying_rate_(float* decaying_rate);
+    void chase_set_cluster_aware_degrees_(int* flag);
+    void chase_set_upperb_scale_rate_(float* upperb_scale_rate);
+
+    void chase_get_version_(char* version, int* len);
+    void chase_has_cuda_(int* flag);
+    void chase_has_nccl_(int* flag);
+    void chase_has_scalapack_(int* flag);
+    void chase_has_mpi_(int* flag);
+    void chase_print_config_(void);
+
+    /* ---- chase_b200 additions (introspection for parity tests and benchmarks) ---- */
+    /* residuals of the last solve (nev+nex values, ordered like ritzv) */
+    void dchase_get_resid_(double* resid);
+    void schase_get_resid_(float* resid);
+    void cchase_get_resid_(float* resid);
+    void zchase_get_resid_(double* resid);
+    /* out[0..15]: iterations, filtered_vecs, hemm_calls, swaps, t_all, t_initvecs, t_lanczos, t_filter, t_qr, t_rr,
+       t_resid, gflop_filter, gflop_total, heev_sweeps, gather_passes, error_flag  (seconds / GFLOP, last solve) */
+    void chase_b200_get_stats_(double* out, int* n);
+    /* record the ChaseBase call trace of subsequent solves (format of oracle/ref_driver.cpp) */
+    void chase_b200_trace_enable_(int* flag);
+    /* copies the '\n'-joined trace of the last solve; returns the byte count needed (without NUL) */
+    size_t chase_b200_trace_copy_(char* buf, size_t cap);
+    /* '\n'-joined CholQR variants chosen during the last solve */
+    size_t chase_b200_qr_log_copy_(char* buf, size_t cap);
+    /* host-side start block used by initVecs in parity mode: the reference CPU backend's mt19937(1337) +
+       normal_distribution stream (reference Impl/chase_cpu/chase_cpu.hpp:296-309), N x m column-major */
+    void chase_b200_start_vectors_d(int64_t N, int64_t m, double* V, int64_t ldv);
+    void chase_b200_start_vectors_s(int64_t N, int64_t m, float* V, int64_t ldv);
+    void chase_b200_start_vectors_z(int64_t N, int64_t m, CHASE_B200_CD* V, int64_t ldv);
+    void chase_b200_start_vectors_c(int64_t N, int64_t m, CHASE_B200_CF* V, int64_t ldv);
+    /* message of the last failed init/solve ("" if none); stats[15] is 1 after a failed solve */
+    size_t chase_b200_last_error_copy_(char* buf, size_t cap);
+    int chase_b200_device_sync(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
