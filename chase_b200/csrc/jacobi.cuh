@@ -21,6 +21,7 @@ struct JRot
 {
     double c, s;
     double ure, uim; // unit phase u
+    double tapq;     // t * |a_pq|: the diagonal moves by -/+ this amount
     int active;
     int pad;
 };
@@ -74,6 +75,7 @@ __device__ __forceinline__ JRot make_rot(double app, double aqq, C apq, double t
     R.s = 0.0;
     R.ure = 1.0;
     R.uim = 0.0;
+    R.tapq = 0.0;
     R.active = 0;
     R.pad = 0;
     const double ab = sqrt(cabs2(apq));
@@ -83,6 +85,7 @@ __device__ __forceinline__ JRot make_rot(double app, double aqq, C apq, double t
     const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
     R.c = 1.0 / sqrt(t * t + 1.0);
     R.s = t * R.c;
+    R.tapq = t * ab;
     store_u(R, phase_of(apq, ab));
     R.active = 1;
     return R;
@@ -165,6 +168,7 @@ __global__ void jacobi_rot_kernel(int n, int np, int r, const C* Gw, JRot* rots,
     R.s = 0.0;
     R.ure = 1.0;
     R.uim = 0.0;
+    R.tapq = 0.0;
     R.active = 0;
     R.pad = 0;
     if (p < n && q < n)
@@ -206,14 +210,17 @@ __global__ void jacobi_apply_kernel(int n, int np, int r, C* Gw, C* Zw, const JR
             b10 = Gw[qa + (long long)pb * n];
         if (va_q && vb_q)
             b11 = Gw[qa + (long long)qb * n];
+        const double app = creal(b00), aqq = creal(b11);
         rot_block<C>(b00, b01, b10, b11, Ra, Rb);
         if (t == b)
         {
-            // annihilated element: set exactly, keep the diagonal real
+            // pivot block: annihilated element set exactly; the diagonal is updated with the
+            // classical small-correction formulas (a_pp - t|a_pq|, a_qq + t|a_pq|) so that its
+            // rounding error scales with the correction, not with |a_pp|
             b01 = czero<C>();
             b10 = czero<C>();
-            b00 = real_only(b00);
-            b11 = real_only(b11);
+            b00 = from_real<C>(app - Ra.tapq);
+            b11 = from_real<C>(aqq + Ra.tapq);
         }
         if (va_p && vb_p)
             Gw[pa + (long long)pb * n] = b00;
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(256) jacobi_small_tridiag_kernel(int n, const 
                 R.s = 0.0;
                 R.ure = 1.0;
                 R.uim = 0.0;
+                R.tapq = 0.0;
                 R.active = 0;
                 R.pad = 0;
                 if (p < n && q < n)
@@ -334,9 +342,14 @@ __global__ void __launch_bounds__(256) jacobi_small_tridiag_kernel(int n, const 
                 double b01 = (vap && vbq) ? G[pa + qb * LD] : 0.0;
                 double b10 = (vaq && vbp) ? G[qa + pb * LD] : 0.0;
                 double b11 = (vaq && vbq) ? G[qa + qb * LD] : 0.0;
+                const double app = b00, aqq = b11;
                 rot_block<double>(b00, b01, b10, b11, Ra, Rb);
                 if (a == b)
+                {
                     b01 = b10 = 0.0;
+                    b00 = app - Ra.tapq;
+                    b11 = aqq + Ra.tapq;
+                }
                 if (vap && vbp)
                     G[pa + pb * LD] = b00;
                 if (vap && vbq)

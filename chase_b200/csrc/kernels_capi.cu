@@ -57,9 +57,12 @@ int hemm_impl(int64_t n, int64_t k, double are, double aim, const void* A, int64
     if (k == 0 || n == 0)
         return 0;
     const C_ alpha = make_comp<C_>(are, aim), beta = make_comp<C_>(bre, bim);
-    if (hemm_tma_supported<T>(n, k, A, lda, B, ldb, C, ldc))
-        return hemm_tma_launch<T>(n, k, alpha, (const T*)A, lda, (const T*)B, ldb, beta, (T*)C, ldc, shift, theta,
-                                  S(stream));
+    if constexpr (std::is_same<T, double>::value || std::is_same<T, cxd>::value)
+    {
+        if (hemm_tma_supported<T>(n, k, A, lda, B, ldb, C, ldc))
+            return hemm_tma_launch<T>(n, k, alpha, (const T*)A, lda, (const T*)B, ldb, beta, (T*)C, ldc, shift,
+                                      theta, S(stream));
+    }
     GemmArgs<T> p{};
     p.M = n;
     p.N = k;
