@@ -358,7 +358,7 @@ int gemm_launch(bool ta, bool tb, GemmArgs<T> p, void* ws, size_t ws_bytes, cuda
     auto launch = [&](auto kern) -> int
     {
         CB2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM_BYTES));
-        kern<<<grid, 256, TL::SMEM_BYTES, st>>>(p);
+        kern<<<grid, 256, TL::SMEM_BYTES, kcount(st)>>>(p);
         CB2_CUDA_OK(cudaGetLastError());
         return 0;
     };
@@ -377,7 +377,7 @@ int gemm_launch(bool ta, bool tb, GemmArgs<T> p, void* ws, size_t ws_bytes, cuda
     {
         long long total = p.M * p.N;
         int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-        gemm_splitk_reduce<T><<<blocks, 256, 0, st>>>(p);
+        gemm_splitk_reduce<T><<<blocks, 256, 0, kcount(st)>>>(p);
         CB2_CUDA_OK(cudaGetLastError());
     }
     return 0;

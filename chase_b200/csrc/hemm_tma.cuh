@@ -451,7 +451,7 @@ inline int hemm_tma_launch(int64_t n, int64_t k, typename Traits<T>::comp alpha,
     const long long ntiles = (long long)p.tiles_m * p.tiles_n;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
-    hemm_tma_kernel<T><<<grid, CF::THREADS, CF::SMEM_BYTES, st>>>(mapA, mapB, p);
+    hemm_tma_kernel<T><<<grid, CF::THREADS, CF::SMEM_BYTES, kcount(st)>>>(mapA, mapB, p);
     CB2_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -19,6 +19,27 @@ namespace
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Optional per-launch timing of the filter HEMM (CUDA events on the launching stream); bench.py turns it on to
+// report the kernel's own TFLOP/s next to the whole-solve numbers.
+struct HemmProfile
+{
+    bool on = false;
+    std::vector<cudaEvent_t> ev; // pairs
+    std::vector<double> flops;
+    size_t used = 0;
+    cudaEvent_t get()
+    {
+        if (used == ev.size())
+        {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev.push_back(e);
+        }
+        return ev[used++];
+    }
+};
+HemmProfile g_hprof;
+
 template <class T>
 int gemm_impl(int ta, int tb, int64_t M, int64_t N, int64_t K, double are, double aim, const void* A, int64_t lda,
               const void* B, int64_t ldb, double bre, double bim, void* C, int64_t ldc, int uplo, void* ws,
@@ -57,6 +78,26 @@ int hemm_impl(int64_t n, int64_t k, double are, double aim, const void* A, int64
     if (k == 0 || n == 0)
         return 0;
     const C_ alpha = make_comp<C_>(are, aim), beta = make_comp<C_>(bre, bim);
+    struct Timed
+    {
+        cudaStream_t st;
+        cudaEvent_t e1 = nullptr;
+        Timed(cudaStream_t s, double fl) : st(s)
+        {
+            if (g_hprof.on)
+            {
+                cudaEvent_t e0 = g_hprof.get();
+                e1 = g_hprof.get();
+                g_hprof.flops.push_back(fl);
+                cudaEventRecord(e0, st);
+            }
+        }
+        ~Timed()
+        {
+            if (e1)
+                cudaEventRecord(e1, st);
+        }
+    } timed(S(stream), 2.0 * (Traits<T>::cplx ? 4.0 : 1.0) * (double)n * (double)n * (double)k);
     if constexpr (std::is_same<T, double>::value || std::is_same<T, cxd>::value)
     {
         if (hemm_tma_supported<T>(n, k, A, lda, B, ldb, C, ldc))
@@ -102,11 +143,11 @@ int potrf_impl(int64_t n, void* Gv, int64_t ldg, int* info_dev, void* stream)
     for (int64_t j0 = 0; j0 < n; j0 += POTRF_NB)
     {
         const int nb = (int)std::min<int64_t>(POTRF_NB, n - j0);
-        potrf_diag_kernel<T><<<1, 256, 0, st>>>(nb, G, ldg, (int)j0, info_dev);
+        potrf_diag_kernel<T><<<1, 256, 0, kcount(st)>>>(nb, G, ldg, (int)j0, info_dev);
         const int64_t rem = n - j0 - nb;
         if (rem > 0)
         {
-            potrf_panel_kernel<T><<<(unsigned)((rem + 127) / 128), 128, 0, st>>>((int)n, nb, G, ldg, (int)j0, info_dev);
+            potrf_panel_kernel<T><<<(unsigned)((rem + 127) / 128), 128, 0, kcount(st)>>>((int)n, nb, G, ldg, (int)j0, info_dev);
             // G[j0+nb:, j0+nb:] -= R[j0:j0+nb, j0+nb:]^H R[j0:j0+nb, j0+nb:]   (upper tiles)
             GemmArgs<T> p{};
             p.M = rem;
@@ -147,7 +188,7 @@ int trsm_impl(int64_t rows, int64_t n, const void* Rv, int64_t ldr, void* Vv, in
     T* X = (T*)Xv;
     T* Rinv = (T*)ws;
     cudaStream_t st = S(stream);
-    trinv_kernel<T><<<(unsigned)nblk, TRSM_NB, 0, st>>>((int)n, TRSM_NB, Rm, ldr, Rinv);
+    trinv_kernel<T><<<(unsigned)nblk, TRSM_NB, 0, kcount(st)>>>((int)n, TRSM_NB, Rm, ldr, Rinv);
     CB2_CUDA_OK(cudaGetLastError());
     for (int64_t b = 0; b < nblk; ++b)
     {
@@ -225,7 +266,7 @@ int heev_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, d
     {
         const long long total = (long long)n * n;
         const int blocks = (int)std::min<long long>((total + 255) / 256, 2368);
-        jacobi_init_kernel<T><<<blocks, 256, 0, st>>>(n, (const T*)Gv, ldg, Gw, Zw, fro2);
+        jacobi_init_kernel<T><<<blocks, 256, 0, kcount(st)>>>(n, (const T*)Gv, ldg, Gw, Zw, fro2);
     }
     int sweep = 0, converged = 0;
     const int max_sweeps = 40;
@@ -235,8 +276,8 @@ int heev_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, d
         CB2_CUDA_OK(cudaMemsetAsync(nrot, 0, sizeof(int), st));
         for (int r = 0; r < np - 1; ++r)
         {
-            jacobi_rot_kernel<C_><<<(h + 127) / 128, 128, 0, st>>>(n, np, r, Gw, rots, fro2, nrot);
-            jacobi_apply_kernel<C_><<<agrid, 128, 0, st>>>(n, np, r, Gw, Zw, rots);
+            jacobi_rot_kernel<C_><<<(h + 127) / 128, 128, 0, kcount(st)>>>(n, np, r, Gw, rots, fro2, nrot);
+            jacobi_apply_kernel<C_><<<agrid, 128, 0, kcount(st)>>>(n, np, r, Gw, Zw, rots);
         }
         int nr = 0;
         CB2_CUDA_OK(cudaMemcpyAsync(&nr, nrot, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -247,7 +288,7 @@ int heev_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, d
             break;
         }
     }
-    jacobi_diag_kernel<C_><<<(n + 255) / 256, 256, 0, st>>>(n, Gw, w_dev);
+    jacobi_diag_kernel<C_><<<(n + 255) / 256, 256, 0, kcount(st)>>>(n, Gw, w_dev);
     std::vector<double> w(n);
     CB2_CUDA_OK(cudaMemcpyAsync(w.data(), w_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
     CB2_CUDA_OK(cudaStreamSynchronize(st));
@@ -257,7 +298,7 @@ int heev_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, d
     for (int i = 0; i < n; ++i)
         w_host[i] = w[perm[i]];
     CB2_CUDA_OK(cudaMemcpyAsync(perm_dev, perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
-    jacobi_gather_kernel<T><<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, st>>>(n, Zw, perm_dev, (T*)Zv, ldz);
+    jacobi_gather_kernel<T><<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, kcount(st)>>>(n, Zw, perm_dev, (T*)Zv, ldz);
     CB2_CUDA_OK(cudaGetLastError());
     CB2_CUDA_OK(cudaStreamSynchronize(st)); // perm (host vector) must outlive the copy
     if (sweeps_out)
@@ -280,17 +321,17 @@ int gemv_impl(int64_t rows, int64_t cols, const void* A, int64_t lda, const void
         T* y = (T*)Y + (int64_t)v * ldy;
         if (nv - v >= 4)
         {
-            gemv_conjT_kernel<T, 4><<<blocks, 256, 0, st>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
+            gemv_conjT_kernel<T, 4><<<blocks, 256, 0, kcount(st)>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
             v += 4;
         }
         else if (nv - v >= 2)
         {
-            gemv_conjT_kernel<T, 2><<<blocks, 256, 0, st>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
+            gemv_conjT_kernel<T, 2><<<blocks, 256, 0, kcount(st)>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
             v += 2;
         }
         else
         {
-            gemv_conjT_kernel<T, 1><<<blocks, 256, 0, st>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
+            gemv_conjT_kernel<T, 1><<<blocks, 256, 0, kcount(st)>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
             v += 1;
         }
     }
@@ -355,7 +396,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (n <= 0)                                                                                                    \
             return 0;                                                                                                  \
-        shift_by_abstrace_kernel<TT><<<1, 256, 0, S(st)>>>((int)n, (TT*)G, ldg, scale, so);                           \
+        shift_by_abstrace_kernel<TT><<<1, 256, 0, kcount(S(st))>>>((int)n, (TT*)G, ldg, scale, so);                           \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
@@ -369,7 +410,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (cols <= 0)                                                                                                 \
             return 0;                                                                                                  \
-        colnorm_kernel<TT><<<(unsigned)cols, 256, 0, S(st)>>>(rows, (const TT*)Xm, ldx, out, take_sqrt);              \
+        colnorm_kernel<TT><<<(unsigned)cols, 256, 0, kcount(S(st))>>>(rows, (const TT*)Xm, ldx, out, take_sqrt);              \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
@@ -378,7 +419,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (rows <= 0 || cols <= 0)                                                                                    \
             return 0;                                                                                                  \
-        lacpy_kernel<TT><<<grid2d(rows, cols), 256, 0, S(st)>>>(rows, cols, (const TT*)src, lds, (TT*)dst, ldd);      \
+        lacpy_kernel<TT><<<grid2d(rows, cols), 256, 0, kcount(S(st))>>>(rows, cols, (const TT*)src, lds, (TT*)dst, ldd);      \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
@@ -387,7 +428,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (rows <= 0 || cnt <= 0)                                                                                     \
             return 0;                                                                                                  \
-        gather_cols_kernel<TT><<<grid2d(rows, cnt), 256, 0, S(st)>>>(rows, cnt, sc, dc, (const TT*)src, lds,          \
+        gather_cols_kernel<TT><<<grid2d(rows, cnt), 256, 0, kcount(S(st))>>>(rows, cnt, sc, dc, (const TT*)src, lds,          \
                                                                       (TT*)dst, ldd);                                  \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
@@ -402,7 +443,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (nv <= 0)                                                                                                   \
             return 0;                                                                                                  \
-        lanczos_step_kernel<TT><<<nv, 1024, 0, S(st)>>>(rows, k, M, (const TT*)v0, (const TT*)v1, (TT*)v2, ld, d, e,  \
+        lanczos_step_kernel<TT><<<nv, 1024, 0, kcount(S(st))>>>(rows, k, M, (const TT*)v0, (const TT*)v1, (TT*)v2, ld, d, e,  \
                                                         rb);                                                           \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
@@ -411,7 +452,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (cols <= 0)                                                                                                 \
             return 0;                                                                                                  \
-        normalize_cols_kernel<TT><<<(unsigned)cols, 1024, 0, S(st)>>>(rows, (TT*)Xm, ldx);                            \
+        normalize_cols_kernel<TT><<<(unsigned)cols, 1024, 0, kcount(S(st))>>>(rows, (TT*)Xm, ldx);                            \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
@@ -420,7 +461,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (rows <= 0 || cols <= 0)                                                                                    \
             return 0;                                                                                                  \
-        rng_normal_kernel<TT><<<1184, 256, 0, S(st)>>>(rows, cols, (TT*)Xm, ldx, seed);                               \
+        rng_normal_kernel<TT><<<1184, 256, 0, kcount(S(st))>>>(rows, cols, (TT*)Xm, ldx, seed);                               \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
@@ -429,7 +470,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (n <= 0)                                                                                                    \
             return 0;                                                                                                  \
-        herm_check_kernel<TT><<<1184, 256, 0, S(st)>>>(n, (const TT*)A, lda, tol, bad);                               \
+        herm_check_kernel<TT><<<1184, 256, 0, kcount(S(st))>>>(n, (const TT*)A, lda, tol, bad);                               \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
@@ -437,7 +478,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (n <= 0)                                                                                                    \
             return 0;                                                                                                  \
-        shift_diag_kernel<TT><<<(unsigned)((n + 255) / 256), 256, 0, S(st)>>>(n, (TT*)A, lda, c);                     \
+        shift_diag_kernel<TT><<<(unsigned)((n + 255) / 256), 256, 0, kcount(S(st))>>>(n, (TT*)A, lda, c);                     \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
@@ -445,7 +486,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         if (n <= 0)                                                                                                    \
             return 0;                                                                                                  \
-        herm_mirror_kernel<TT><<<1184, 256, 0, S(st)>>>(n, (TT*)A, lda, from_upper);                                  \
+        herm_mirror_kernel<TT><<<1184, 256, 0, kcount(S(st))>>>(n, (TT*)A, lda, from_upper);                                  \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }
@@ -462,7 +503,7 @@ extern "C" int chase_b200_tridiag_eig(int n, int batch, const double* d, const d
         return 0;
     if (n > JSMALL_MAX)
         return -2;
-    jacobi_small_tridiag_kernel<<<batch, 256, 0, S(st)>>>(n, d, e, ldde, w, Z, nullptr);
+    jacobi_small_tridiag_kernel<<<batch, 256, 0, kcount(S(st))>>>(n, d, e, ldde, w, Z, nullptr);
     CB2_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -523,6 +564,39 @@ extern "C" double chase_b200_dmma_peak(int iters, void* st)
     cudaFree(sink);
     const double flops = 2.0 * 8 * 8 * 4 * 8.0 * (double)iters * 8.0 * blocks; // per DMMA 512 flop, 8/iter/warp, 8 warps
     return flops / (ms * 1e-3);
+}
+
+extern "C" unsigned long long chase_b200_launch_count(void) { return launch_counter(); }
+
+extern "C" int chase_b200_hemm_profile_enable(int on)
+{
+    g_hprof.on = (on != 0);
+    g_hprof.used = 0;
+    g_hprof.flops.clear();
+    return 0;
+}
+
+extern "C" int chase_b200_hemm_profile_read(double* out4)
+{
+    if (cudaDeviceSynchronize() != cudaSuccess)
+        return -1;
+    double ms = 0, fl = 0, mx = 0;
+    const size_t n = g_hprof.flops.size();
+    for (size_t i = 0; i < n; ++i)
+    {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, g_hprof.ev[2 * i], g_hprof.ev[2 * i + 1]) != cudaSuccess)
+            return -1;
+        ms += t;
+        fl += g_hprof.flops[i];
+        if (t > mx)
+            mx = t;
+    }
+    out4[0] = (double)n;
+    out4[1] = ms;
+    out4[2] = fl;
+    out4[3] = mx;
+    return 0;
 }
 
 extern "C" const char* chase_b200_version(void) { return "chase_b200 0.1 (sm_100a)"; }

@@ -30,6 +30,8 @@ struct LastRun
 };
 LastRun g_last;
 bool g_trace = false;
+int g_matrix_resident = 0; // chase_b200_set_matrix_resident_
+int g_device_rng = -1;     // chase_b200_set_device_rng_ (-1: leave the backend's default / env)
 
 template <class T>
 struct Seq
@@ -93,6 +95,9 @@ struct Seq
         config.SetApprox(mode == 'A');
         config.SetCholQR(qr == 'C');
         solver->clear_logs();
+        solver->keep_device_matrix(g_matrix_resident != 0);
+        if (g_device_rng >= 0)
+            solver->use_device_rng(g_device_rng != 0);
         chase::PerformanceDecoratorChase<T> perf(solver.get());
         perf.EnableTrace(g_trace);
         g_last.error.clear();
@@ -394,6 +399,8 @@ extern "C"
             out[i] = g_last.stats[i];
     }
     void chase_b200_trace_enable_(int* flag) { g_trace = (*flag != 0); }
+    void chase_b200_set_matrix_resident_(int* flag) { g_matrix_resident = *flag; }
+    void chase_b200_set_device_rng_(int* flag) { g_device_rng = *flag; }
     size_t chase_b200_trace_copy_(char* buf, size_t cap) { return copy_out(g_last.trace, buf, cap); }
     size_t chase_b200_qr_log_copy_(char* buf, size_t cap) { return copy_out(g_last.qr_log, buf, cap); }
     size_t chase_b200_last_error_copy_(char* buf, size_t cap) { return copy_out(g_last.error, buf, cap); }

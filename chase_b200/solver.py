@@ -100,7 +100,7 @@ class ChASE:
         return self
 
     def solve(self, deg: int = 20, tol: float | None = None, mode: str = "R", opt: str = "S", qr: str = "C",
-              trace: bool = False) -> SolveResult:
+              trace: bool = False, copy: bool = True) -> SolveResult:
         L = self._lib
         if tol is None:
             tol = 1e-10 if self.rdt == np.float64 else 1e-5
@@ -116,7 +116,9 @@ class ChASE:
         L.chase_b200_get_stats_(_p(st), _i(16))
         if st[15] != 0:
             raise RuntimeError("chase_b200: solve failed: " + self._last_error())
-        res = SolveResult(self.ritzv.copy(), resid, self.V.copy(order="F"), dict(zip(STAT_NAMES, st.tolist())))
+        # copy=False hands out the caller-owned V itself (what a C caller sees), avoiding an N x (nev+nex) host copy
+        res = SolveResult(self.ritzv.copy(), resid, self.V.copy(order="F") if copy else self.V,
+                          dict(zip(STAT_NAMES, st.tolist())))
         if trace:
             n = L.chase_b200_trace_copy_(None, 0)
             buf = ctypes.create_string_buffer(n + 1)

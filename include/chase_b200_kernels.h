@@ -112,6 +112,13 @@ extern "C"
     /* FP64 tensor-pipe microbenchmark: runs `iters` register-resident DMMA.8x8x4 per warp on every SM and
        returns the achieved FLOP/s (the roofline denominator for the filter; MEASURED_PEAKS.json has no FP64). */
     double chase_b200_dmma_peak(int iters, void* stream);
+    /* Number of product kernels launched by this library so far (process-wide; bench.py's gpu_launches). */
+    unsigned long long chase_b200_launch_count(void);
+    /* Per-launch CUDA-event timing of the filter HEMM kernel on its launching stream.  enable(1) resets and
+       starts recording, read() synchronises the device and returns {launches, total ms, total algorithmic
+       flop (2 f n^2 k per launch), longest single launch ms}. */
+    int chase_b200_hemm_profile_enable(int on);
+    int chase_b200_hemm_profile_read(double* out4);
     const char* chase_b200_version(void);
 
 #ifdef __cplusplus

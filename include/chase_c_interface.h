@@ -110,6 +110,13 @@ extern "C"
     /* message of the last failed init/solve ("" if none); stats[15] is 1 after a failed solve */
     size_t chase_b200_last_error_copy_(char* buf, size_t cap);
     int chase_b200_device_sync(void);
+    /* flag != 0: subsequent solves do NOT re-upload the host matrix H when a copy from an earlier solve is already
+       on the device (default 0 = the reference's behaviour: H is re-read at every solve, chase_gpu.hpp:536) */
+    void chase_b200_set_matrix_resident_(int* flag);
+    /* flag != 0: random start vectors come from the on-device Philox generator (what the reference GPU backend
+       does with cuRAND, chase_gpu.hpp:509-533); 0 (default): the reference CPU backend's mt19937 stream, which is
+       what makes iteration counts identical to the reference CPU solver */
+    void chase_b200_set_device_rng_(int* flag);
 
 #ifdef __cplusplus
 }
