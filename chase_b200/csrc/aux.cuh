@@ -35,6 +35,57 @@ __global__ void gather_cols_kernel(long long rows, int cnt, const int* scols, co
     }
 }
 
+// dst[i, j] = src[src_row[i], j] for every i with src_row[i] >= 0.  One primitive for all layout changes of the
+// distributed backend (pick local rows out of an all-gathered panel, un-permute block-cyclic pieces into global
+// order); replaces the per-block broadcasts of the reference's redistributeImpl
+// (linalg/distMatrix/distMultiVector.hpp:2817-2909).
+// piece_stride > 0: the source is an all-gathered stack of pieces, each a column-major (lds x cols) panel stored
+// piece_stride elements apart; src_row = piece * lds + row inside the piece.
+template <class T>
+__global__ void gather_rows_kernel(long long rows, long long cols, const long long* src_row, const T* src,
+                                   long long lds, long long piece_stride, T* dst, long long ldd)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+         i += (long long)gridDim.x * blockDim.x)
+    {
+        long long s = src_row[i];
+        if (s < 0)
+            continue;
+        if (piece_stride > 0)
+        {
+            const long long piece = s / lds;
+            s = piece * piece_stride + (s - piece * lds);
+        }
+        for (long long j = blockIdx.y; j < cols; j += gridDim.y)
+            dst[i + j * ldd] = src[s + j * lds];
+    }
+}
+
+// C[:, j] += g * gvec[j] * E[:, j]   (residual block R = A V - V diag(theta) when A V and V are already at hand)
+template <class T>
+__global__ void axpy_cols_kernel(long long rows, long long cols, const double* gvec, typename Traits<T>::comp g,
+                                 const T* E, long long lde, T* Cm, long long ldc)
+{
+    using C = typename Traits<T>::comp;
+    for (long long j = blockIdx.y; j < cols; j += gridDim.y)
+    {
+        const C f = cmul(gvec[j], g);
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+             i += (long long)gridDim.x * blockDim.x)
+            Cm[i + j * ldc] = narrow<T>(cadd((C)widen(Cm[i + j * ldc]), cmul(f, (C)widen(E[i + j * lde]))));
+    }
+}
+
+// A[lin[t]] += c for the local copies of global diagonal entries (reference chase_shift_mgpu_matrix,
+// cuda/shiftDiagonal.cu:100-150; index lists built like Impl/pchase_gpu/pchase_gpu.hpp:340-409)
+template <class T>
+__global__ void shift_diag_list_kernel(long long cnt, const long long* lin, T* A, double c)
+{
+    using C = typename Traits<T>::comp;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < cnt; t += (long long)gridDim.x * blockDim.x)
+        A[lin[t]] = narrow<T>(cadd((C)widen(A[lin[t]]), from_real<C>(c)));
+}
+
 // out[j] = ||X[:, j]||_2 (take_sqrt) or its square
 template <class T>
 __global__ void __launch_bounds__(256) colnorm_kernel(long long rows, const T* X, long long ldx, double* out,
@@ -219,6 +270,26 @@ __global__ void rng_normal_kernel(long long rows, long long cols, T* X, long lon
         double a, b;
         philox_normal2(seed, (unsigned long long)idx, a, b);
         const long long i = idx % rows, j = idx / rows;
+        if constexpr (Traits<T>::cplx)
+            X[i + j * ldx] = narrow<T>(cxd{a, b});
+        else
+            X[i + j * ldx] = narrow<T>(a);
+    }
+}
+
+// Same generator addressed by GLOBAL element index grow[i] + j * nglobal: the start block does not depend on how the
+// rows are distributed (1 GPU and r x c grids draw the same matrix).
+template <class T>
+__global__ void rng_normal_rows_kernel(long long rows, long long cols, const long long* grow, long long nglobal, T* X,
+                                       long long ldx, unsigned long long seed)
+{
+    const long long total = rows * cols;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x)
+    {
+        const long long i = idx % rows, j = idx / rows;
+        double a, b;
+        philox_normal2(seed, (unsigned long long)(grow[i] + j * nglobal), a, b);
         if constexpr (Traits<T>::cplx)
             X[i + j * ldx] = narrow<T>(cxd{a, b});
         else

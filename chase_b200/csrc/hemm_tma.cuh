@@ -20,6 +20,12 @@
 //                 folded diagonal shift) goes register -> global with 16-byte
 //                 accesses while the producer already streams the next tile.
 //
+// The same kernel serves the distributed backend (pChASEGPU): A may be a
+// rectangular local block (M x K) and TA selects C <- alpha * A^H * B + beta * C
+// for the column-layout -> row-layout step of the reference's distributed HEMM
+// (linalg/internal/nccl/hemm.hpp:325-332).  With TA the A tile is K-major like
+// the B tile (one 128-row TMA box per stage) and uses the B-style fragment map.
+//
 // tcgen05/TMEM cannot be used here: tcgen05.mma has no f64 kind (ptxas rejects
 // it), so the FP64 tensor path on Blackwell is warp-level DMMA.
 //
@@ -101,8 +107,8 @@ template <class T>
 struct HemmParams
 {
     using C_ = typename Traits<T>::comp;
-    long long n, k;     // A is n x n, panels n x k
-    const T* B;         // only for the folded shift term in the epilogue
+    long long M, K, k;  // op(A) is M x K, B is K x k, C is M x k
+    const T* B;         // only for the folded shift term in the epilogue (square, non-transposed case)
     long long ldb;
     T* C;
     long long ldc;
@@ -112,7 +118,7 @@ struct HemmParams
     int tiles_m, tiles_n;
 };
 
-template <class T>
+template <class T, bool TA>
 __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     hemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const HemmParams<T> p)
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     __syncthreads();
 
     const long long ntiles = (long long)p.tiles_m * p.tiles_n;
-    const int nkt = (int)((p.n + BK - 1) / BK);
+    const int nkt = (int)((p.K + BK - 1) / BK);
 
     if (warp == CF::CONSUMER_WARPS)
     {
@@ -165,9 +171,14 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
                     mbar_expect_tx(full, CF::STAGE_BYTES);
                     const uint32_t sa = base + s * CF::STAGE_BYTES;
                     const uint32_t sb = sa + CF::A_BYTES;
+                    if constexpr (TA)
+                        tma_load_2d(sa, &mapA, full, kt * BK * IMUL, m0);
+                    else
+                    {
 #pragma unroll
-                    for (int b = 0; b < BM / EPB; ++b)
-                        tma_load_2d(sa + b * (BK * 128), &mapA, full, (m0 + b * EPB) * IMUL, kt * BK);
+                        for (int b = 0; b < BM / EPB; ++b)
+                            tma_load_2d(sa + b * (BK * 128), &mapA, full, (m0 + b * EPB) * IMUL, kt * BK);
+                    }
                     tma_load_2d(sb, &mapB, full, kt * BK * IMUL, n0);
                 }
             }
@@ -215,11 +226,21 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
                 {
-                    const int m = wm * WM + 8 * i + c;
-                    const int mblk = m / EPB, min_ = m % EPB;
-                    const int byte_in = min_ * ELEM;
-                    const int off = (mblk * BK + kin) * 128 + ((((byte_in >> 4) ^ k7) << 4) | (byte_in & 15));
-                    fa[i] = *reinterpret_cast<const C_*>(sa + off);
+                    if constexpr (TA)
+                    {
+                        const int m = wm * WM + 8 * i + ncol;
+                        const int byte_in = kin * ELEM;
+                        const int off = m * 128 + ((((byte_in >> 4) ^ (m & 7)) << 4) | (byte_in & 15));
+                        fa[i] = *reinterpret_cast<const C_*>(sa + off);
+                    }
+                    else
+                    {
+                        const int m = wm * WM + 8 * i + c;
+                        const int mblk = m / EPB, min_ = m % EPB;
+                        const int byte_in = min_ * ELEM;
+                        const int off = (mblk * BK + kin) * 128 + ((((byte_in >> 4) ^ k7) << 4) | (byte_in & 15));
+                        fa[i] = *reinterpret_cast<const C_*>(sa + off);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < NJ; ++j)
@@ -242,13 +263,16 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j)
                     {
-                        const double bre = fb[j].re, bim = fb[j].im, bimn = -fb[j].im;
+                        // TA: the A operand enters conjugated: (ar - i ai)(br + i bi)
+                        const double bre = fb[j].re, bim = fb[j].im;
+                        const double s_ri = TA ? fb[j].im : -fb[j].im; // multiplies a.im into the real part
+                        const double s_ir = TA ? -fb[j].re : fb[j].re; // multiplies a.im into the imaginary part
 #pragma unroll
                         for (int i = 0; i < MI; ++i)
                         {
                             dmma884(accr[j][i][0], accr[j][i][1], bre, fa[i].re);
-                            dmma884(accr[j][i][0], accr[j][i][1], bimn, fa[i].im);
-                            dmma884(acci[j][i][0], acci[j][i][1], bre, fa[i].im);
+                            dmma884(accr[j][i][0], accr[j][i][1], s_ri, fa[i].im);
+                            dmma884(acci[j][i][0], acci[j][i][1], s_ir, fa[i].im);
                             dmma884(acci[j][i][0], acci[j][i][1], bim, fa[i].re);
                         }
                     }
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
 
         // ------------------------------ epilogue ------------------------------
         const bool has_beta = cnonzero(p.beta);
-        const bool has_shift = (p.theta != nullptr) || (p.shift != 0.0);
+        const bool has_shift = !TA && ((p.theta != nullptr) || (p.shift != 0.0));
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
         {
@@ -277,8 +301,10 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
 #pragma unroll
             for (int i = 0; i < MI; ++i)
             {
-                const long long m = m0 + wm * WM + 8 * i + 2 * q;
-                if (m >= p.n)
+                // TA: operand column c' of the A fragment holds row ncol(c') (see the fragment map above)
+                const int mq = TA ? ((q & 1) << 2 | (q & 2)) : 2 * q; // ncol(2q) = {0,4,2,6}
+                const long long m = m0 + wm * WM + 8 * i + mq;
+                if (m >= p.M)
                     continue;
                 C_ o0, o1;
                 if constexpr (CPLX)
@@ -291,7 +317,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
                     o0 = p.alpha * accr[j][i][0];
                     o1 = p.alpha * accr[j][i][1];
                 }
-                const bool pair = (m + 1 < p.n);
+                const bool pair = (m + 1 < p.M);
                 if constexpr (!CPLX)
                 {
                     if (pair)
@@ -374,15 +400,15 @@ inline bool hemm_tma_disabled()
 
 // FP64 storage only (TMA moves raw bytes; FP32 storage is widened by the generic kernel).
 template <class T>
-inline bool hemm_tma_supported(int64_t n, int64_t k, const void* A, int64_t lda, const void* B, int64_t ldb,
-                               const void* C, int64_t ldc)
+inline bool hemm_tma_supported(int64_t M, int64_t K, int64_t k, const void* A, int64_t lda, const void* B,
+                               int64_t ldb, const void* C, int64_t ldc)
 {
     if (!(std::is_same<T, double>::value || std::is_same<T, cxd>::value))
         return false;
     if (hemm_tma_disabled() || get_encode_fn() == nullptr)
         return false;
     const int64_t per16 = 16 / (int64_t)sizeof(T) > 0 ? 16 / (int64_t)sizeof(T) : 1; // elements per 16 B
-    if (n < 256 || k < 8)
+    if (M < 256 || K < 256 || k < 8)
         return false; // tiny problems: launch-bound anyway
     if (lda % per16 || ldb % per16 || ldc % per16)
         return false;
@@ -392,9 +418,9 @@ inline bool hemm_tma_supported(int64_t n, int64_t k, const void* A, int64_t lda,
 }
 
 template <class T>
-inline int hemm_tma_launch(int64_t n, int64_t k, typename Traits<T>::comp alpha, const T* A, int64_t lda, const T* B,
-                           int64_t ldb, typename Traits<T>::comp beta, T* C, int64_t ldc, double shift,
-                           const double* theta, cudaStream_t st)
+inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Traits<T>::comp alpha, const T* A,
+                           int64_t lda, const T* B, int64_t ldb, typename Traits<T>::comp beta, T* C, int64_t ldc,
+                           double shift, const double* theta, cudaStream_t st)
 {
     constexpr bool CPLX = Traits<T>::cplx;
     using CF = HemmCfg<CPLX>;
@@ -405,9 +431,10 @@ inline int hemm_tma_launch(int64_t n, int64_t k, typename Traits<T>::comp alpha,
     const cuuint64_t inner_mul = CPLX ? 2 : 1;
     CUtensorMap mapA, mapB;
     {
-        cuuint64_t dims[2] = {(cuuint64_t)n * inner_mul, (cuuint64_t)n};
+        // stored A is (M x K) column-major, or (K x M) when op(A) = A^H
+        cuuint64_t dims[2] = {(cuuint64_t)(ta ? K : M) * inner_mul, (cuuint64_t)(ta ? M : K)};
         cuuint64_t strides[1] = {(cuuint64_t)lda * sizeof(T)};
-        cuuint32_t box[2] = {16, (cuuint32_t)CF::BK}; // 16 doubles = 128 B
+        cuuint32_t box[2] = {16, (cuuint32_t)(ta ? CF::BM : CF::BK)}; // 16 doubles = 128 B
         cuuint32_t es[2] = {1, 1};
         CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A, dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -419,7 +446,7 @@ inline int hemm_tma_launch(int64_t n, int64_t k, typename Traits<T>::comp alpha,
         }
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)n * inner_mul, (cuuint64_t)k};
+        cuuint64_t dims[2] = {(cuuint64_t)K * inner_mul, (cuuint64_t)k};
         cuuint64_t strides[1] = {(cuuint64_t)ldb * sizeof(T)};
         cuuint32_t box[2] = {16, (cuuint32_t)CF::BN};
         cuuint32_t es[2] = {1, 1};
@@ -433,7 +460,8 @@ inline int hemm_tma_launch(int64_t n, int64_t k, typename Traits<T>::comp alpha,
         }
     }
     HemmParams<T> p;
-    p.n = n;
+    p.M = M;
+    p.K = K;
     p.k = k;
     p.B = B;
     p.ldb = ldb;
@@ -443,15 +471,25 @@ inline int hemm_tma_launch(int64_t n, int64_t k, typename Traits<T>::comp alpha,
     p.beta = beta;
     p.shift = shift;
     p.theta = theta;
-    p.tiles_m = (int)((n + CF::BM - 1) / CF::BM);
+    p.tiles_m = (int)((M + CF::BM - 1) / CF::BM);
     p.tiles_n = (int)((k + CF::BN - 1) / CF::BN);
     int dev = 0, sms = 0;
     CB2_CUDA_OK(cudaGetDevice(&dev));
     CB2_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long ntiles = (long long)p.tiles_m * p.tiles_n;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
-    CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
-    hemm_tma_kernel<T><<<grid, CF::THREADS, CF::SMEM_BYTES, kcount(st)>>>(mapA, mapB, p);
+    if (ta)
+    {
+        CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         CF::SMEM_BYTES));
+        hemm_tma_kernel<T, true><<<grid, CF::THREADS, CF::SMEM_BYTES, kcount(st)>>>(mapA, mapB, p);
+    }
+    else
+    {
+        CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         CF::SMEM_BYTES));
+        hemm_tma_kernel<T, false><<<grid, CF::THREADS, CF::SMEM_BYTES, kcount(st)>>>(mapA, mapB, p);
+    }
     CB2_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -69,13 +69,16 @@ int gemm_impl(int ta, int tb, int64_t M, int64_t N, int64_t K, double are, doubl
 }
 
 template <class T>
-int hemm_impl(int64_t n, int64_t k, double are, double aim, const void* A, int64_t lda, const void* B, int64_t ldb,
-              double bre, double bim, void* C, int64_t ldc, double shift, const double* theta, void* stream)
+int hemm_rect_impl(int ta, int64_t M, int64_t K, int64_t k, double are, double aim, const void* A, int64_t lda,
+                   const void* B, int64_t ldb, double bre, double bim, void* C, int64_t ldc, double shift,
+                   const double* theta, void* stream)
 {
     using C_ = typename Traits<T>::comp;
-    if (n < 0 || k < 0)
+    if (M < 0 || K < 0 || k < 0)
         return -2;
-    if (k == 0 || n == 0)
+    if ((theta || shift != 0.0) && (ta || M != K))
+        return -2; // the folded diagonal shift needs B and C to share row coordinates
+    if (k == 0 || M == 0)
         return 0;
     const C_ alpha = make_comp<C_>(are, aim), beta = make_comp<C_>(bre, bim);
     struct Timed
@@ -97,17 +100,17 @@ int hemm_impl(int64_t n, int64_t k, double are, double aim, const void* A, int64
             if (e1)
                 cudaEventRecord(e1, st);
         }
-    } timed(S(stream), 2.0 * (Traits<T>::cplx ? 4.0 : 1.0) * (double)n * (double)n * (double)k);
+    } timed(S(stream), 2.0 * (Traits<T>::cplx ? 4.0 : 1.0) * (double)M * (double)K * (double)k);
     if constexpr (std::is_same<T, double>::value || std::is_same<T, cxd>::value)
     {
-        if (hemm_tma_supported<T>(n, k, A, lda, B, ldb, C, ldc))
-            return hemm_tma_launch<T>(n, k, alpha, (const T*)A, lda, (const T*)B, ldb, beta, (T*)C, ldc, shift,
-                                      theta, S(stream));
+        if (K > 0 && hemm_tma_supported<T>(M, K, k, A, lda, B, ldb, C, ldc))
+            return hemm_tma_launch<T>(ta != 0, M, K, k, alpha, (const T*)A, lda, (const T*)B, ldb, beta, (T*)C, ldc,
+                                      shift, theta, S(stream));
     }
     GemmArgs<T> p{};
-    p.M = n;
+    p.M = M;
     p.N = k;
-    p.K = n;
+    p.K = K;
     p.A = (const T*)A;
     p.lda = lda;
     p.B = (const T*)B;
@@ -131,7 +134,14 @@ int hemm_impl(int64_t n, int64_t k, double are, double aim, const void* A, int64
         p.gvec = nullptr;
         p.gscale = cmul(-shift, alpha);
     }
-    return gemm_launch<T>(false, false, p, nullptr, 0, S(stream));
+    return gemm_launch<T>(ta != 0, false, p, nullptr, 0, S(stream));
+}
+
+template <class T>
+int hemm_impl(int64_t n, int64_t k, double are, double aim, const void* A, int64_t lda, const void* B, int64_t ldb,
+              double bre, double bim, void* C, int64_t ldc, double shift, const double* theta, void* stream)
+{
+    return hemm_rect_impl<T>(0, n, n, k, are, aim, A, lda, B, ldb, bre, bim, C, ldc, shift, theta, stream);
 }
 
 template <class T>
@@ -383,6 +393,12 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     {                                                                                                                  \
         return hemm_impl<TT>(n, k, are, aim, A, lda, B, ldb, bre, bim, C, ldc, shift, theta, st);                     \
     }                                                                                                                  \
+    extern "C" int chase_b200_hemm_rect_##X(int ta, int64_t M, int64_t K, int64_t k, double are, double aim,          \
+                                            const void* A, int64_t lda, const void* B, int64_t ldb, double bre,       \
+                                            double bim, void* C, int64_t ldc, void* st)                               \
+    {                                                                                                                  \
+        return hemm_rect_impl<TT>(ta, M, K, k, are, aim, A, lda, B, ldb, bre, bim, C, ldc, 0.0, nullptr, st);         \
+    }                                                                                                                  \
     extern "C" int chase_b200_potrf_##X(int64_t n, void* G, int64_t ldg, int* info, void* st)                         \
     {                                                                                                                  \
         return potrf_impl<TT>(n, G, ldg, info, st);                                                                    \
@@ -430,6 +446,45 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
             return 0;                                                                                                  \
         gather_cols_kernel<TT><<<grid2d(rows, cnt), 256, 0, kcount(S(st))>>>(rows, cnt, sc, dc, (const TT*)src, lds,          \
                                                                       (TT*)dst, ldd);                                  \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_gather_rows_##X(int64_t rows, int64_t cols, const int64_t* src_row, const void* src,    \
+                                              int64_t lds, int64_t piece_stride, void* dst, int64_t ldd, void* st)    \
+    {                                                                                                                  \
+        if (rows <= 0 || cols <= 0)                                                                                    \
+            return 0;                                                                                                  \
+        gather_rows_kernel<TT><<<grid2d(rows, cols), 256, 0, kcount(S(st))>>>(                                        \
+            rows, cols, (const long long*)src_row, (const TT*)src, lds, piece_stride, (TT*)dst, ldd);                  \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_axpy_cols_##X(int64_t rows, int64_t cols, const double* gvec, double gre, double gim,   \
+                                            const void* E, int64_t lde, void* Cm, int64_t ldc, void* st)              \
+    {                                                                                                                  \
+        if (rows <= 0 || cols <= 0)                                                                                    \
+            return 0;                                                                                                  \
+        axpy_cols_kernel<TT><<<grid2d(rows, cols), 256, 0, kcount(S(st))>>>(                                          \
+            rows, cols, gvec, make_comp<typename Traits<TT>::comp>(gre, gim), (const TT*)E, lde, (TT*)Cm, ldc);        \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_shift_diag_list_##X(int64_t cnt, const int64_t* lin, void* A, double c, void* st)       \
+    {                                                                                                                  \
+        if (cnt <= 0)                                                                                                  \
+            return 0;                                                                                                  \
+        shift_diag_list_kernel<TT><<<(unsigned)std::min<int64_t>((cnt + 255) / 256, 1184), 256, 0, kcount(S(st))>>>(  \
+            cnt, (const long long*)lin, (TT*)A, c);                                                                    \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_rng_normal_rows_##X(int64_t rows, int64_t cols, const int64_t* grow, int64_t nglobal,   \
+                                                  void* Xm, int64_t ldx, uint64_t seed, void* st)                     \
+    {                                                                                                                  \
+        if (rows <= 0 || cols <= 0)                                                                                    \
+            return 0;                                                                                                  \
+        rng_normal_rows_kernel<TT><<<1184, 256, 0, kcount(S(st))>>>(rows, cols, (const long long*)grow, nglobal,      \
+                                                                      (TT*)Xm, ldx, seed);                             \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
@@ -531,10 +586,10 @@ extern "C" int chase_b200_hemm_path(int code, int64_t n, int64_t k, int64_t lda,
     const void* al = reinterpret_cast<const void*>(uintptr_t(1024));
     switch (code)
     {
-        case 0: return hemm_tma_supported<float>(n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
-        case 1: return hemm_tma_supported<double>(n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
-        case 2: return hemm_tma_supported<cxf>(n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
-        case 3: return hemm_tma_supported<cxd>(n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
+        case 0: return hemm_tma_supported<float>(n, n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
+        case 1: return hemm_tma_supported<double>(n, n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
+        case 2: return hemm_tma_supported<cxf>(n, n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
+        case 3: return hemm_tma_supported<cxd>(n, n, k, al, lda, al, ldb, al, ldc) ? 1 : 0;
     }
     return 0;
 }

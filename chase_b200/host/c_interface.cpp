@@ -6,8 +6,11 @@
 // for every solve.
 #include "../../include/chase_c_interface.h"
 
+#include "../../include/chase_b200_comm.h"
+
 #include "algorithm.hpp"
 #include "chase_gpu.hpp"
+#include "pchase_gpu.hpp"
 #include "performance.hpp"
 
 #include <complex>
@@ -32,6 +35,70 @@ LastRun g_last;
 bool g_trace = false;
 int g_matrix_resident = 0; // chase_b200_set_matrix_resident_
 int g_device_rng = -1;     // chase_b200_set_device_rng_ (-1: leave the backend's default / env)
+
+// shared by the sequential and the distributed entry points (reference chase_c_interface.cpp:443-491)
+template <class T, class Backend>
+void run_solve(Backend* solver, std::size_t N, int deg, chase::Base<T> tol, char mode, char opt, char qr,
+               double /*unused*/)
+{
+    auto& config = solver->GetConfig();
+    config.SetTol(tol);
+    config.SetDeg((std::size_t)deg);
+    config.SetOpt(opt == 'S');
+    config.SetApprox(mode == 'A');
+    config.SetCholQR(qr == 'C');
+    solver->clear_logs();
+    solver->keep_device_matrix(g_matrix_resident != 0);
+    if (g_device_rng >= 0)
+        solver->use_device_rng(g_device_rng != 0);
+    chase::PerformanceDecoratorChase<T> perf(solver);
+    perf.EnableTrace(g_trace);
+    g_last.error.clear();
+    try
+    {
+        chase::Solve(&perf);
+    }
+    catch (const std::exception& e)
+    {
+        // C callers cannot catch: report, flag (stats[15] = 1) and return
+        std::fprintf(stderr, "chase_b200: solve failed: %s\n", e.what());
+        g_last.error = e.what();
+    }
+
+    auto& pd = perf.GetPerfData();
+    const int factor = chase::is_complex_t<T>::value ? 4 : 1;
+    double* s = g_last.stats;
+    s[0] = (double)pd.get_iter_count();
+    s[1] = (double)pd.get_filtered_vecs();
+    s[2] = (double)perf.HemmCalls();
+    s[3] = (double)perf.Swaps();
+    s[4] = pd.seconds(chase::ChasePerfData::All);
+    s[5] = pd.seconds(chase::ChasePerfData::InitVecs);
+    s[6] = pd.seconds(chase::ChasePerfData::Lanczos);
+    s[7] = pd.seconds(chase::ChasePerfData::Filter);
+    s[8] = pd.seconds(chase::ChasePerfData::Qr);
+    s[9] = pd.seconds(chase::ChasePerfData::Rr);
+    s[10] = pd.seconds(chase::ChasePerfData::Resid);
+    s[11] = pd.get_filter_flops(N, factor);
+    s[12] = pd.get_flops(N, config.GetLanczosIter(), config.GetNumLanczos(), factor);
+    s[13] = (double)solver->heev_sweeps();
+    s[14] = (double)solver->gather_passes();
+    s[15] = g_last.error.empty() ? 0.0 : 1.0;
+    g_last.trace.clear();
+    for (auto& l : perf.Trace())
+    {
+        g_last.trace += l;
+        g_last.trace += '\n';
+    }
+    g_last.qr_log.clear();
+    for (auto& l : solver->qr_log())
+    {
+        g_last.qr_log += l;
+        g_last.qr_log += '\n';
+    }
+    if (std::getenv("CHASE_B200_VERBOSE") && solver->get_rank() == 0)
+        pd.print(N, factor);
+}
 
 template <class T>
 struct Seq
@@ -86,65 +153,8 @@ struct Seq
     }
     void solve(int deg, R tol, char mode, char opt, char qr)
     {
-        if (!solver)
-            return;
-        auto& config = solver->GetConfig();
-        config.SetTol(tol);
-        config.SetDeg((std::size_t)deg);
-        config.SetOpt(opt == 'S');
-        config.SetApprox(mode == 'A');
-        config.SetCholQR(qr == 'C');
-        solver->clear_logs();
-        solver->keep_device_matrix(g_matrix_resident != 0);
-        if (g_device_rng >= 0)
-            solver->use_device_rng(g_device_rng != 0);
-        chase::PerformanceDecoratorChase<T> perf(solver.get());
-        perf.EnableTrace(g_trace);
-        g_last.error.clear();
-        try
-        {
-            chase::Solve(&perf);
-        }
-        catch (const std::exception& e)
-        {
-            // C callers cannot catch: report, flag (stats[15] = 1) and return
-            std::fprintf(stderr, "chase_b200: solve failed: %s\n", e.what());
-            g_last.error = e.what();
-        }
-
-        auto& pd = perf.GetPerfData();
-        const int factor = chase::is_complex_t<T>::value ? 4 : 1;
-        double* s = g_last.stats;
-        s[0] = (double)pd.get_iter_count();
-        s[1] = (double)pd.get_filtered_vecs();
-        s[2] = (double)perf.HemmCalls();
-        s[3] = (double)perf.Swaps();
-        s[4] = pd.seconds(chase::ChasePerfData::All);
-        s[5] = pd.seconds(chase::ChasePerfData::InitVecs);
-        s[6] = pd.seconds(chase::ChasePerfData::Lanczos);
-        s[7] = pd.seconds(chase::ChasePerfData::Filter);
-        s[8] = pd.seconds(chase::ChasePerfData::Qr);
-        s[9] = pd.seconds(chase::ChasePerfData::Rr);
-        s[10] = pd.seconds(chase::ChasePerfData::Resid);
-        s[11] = pd.get_filter_flops(N, factor);
-        s[12] = pd.get_flops(N, config.GetLanczosIter(), config.GetNumLanczos(), factor);
-        s[13] = (double)solver->heev_sweeps();
-        s[14] = (double)solver->gather_passes();
-        s[15] = g_last.error.empty() ? 0.0 : 1.0;
-        g_last.trace.clear();
-        for (auto& l : perf.Trace())
-        {
-            g_last.trace += l;
-            g_last.trace += '\n';
-        }
-        g_last.qr_log.clear();
-        for (auto& l : solver->qr_log())
-        {
-            g_last.qr_log += l;
-            g_last.qr_log += '\n';
-        }
-        if (std::getenv("CHASE_B200_VERBOSE"))
-            pd.print(N, factor);
+        if (solver)
+            run_solve<T>(solver.get(), N, deg, tol, mode, opt, qr, 1.0);
     }
     void get_eigenpairs(T* out, int ld, R* ritz_out)
     {
@@ -164,10 +174,99 @@ struct Seq
     }
 };
 
+// Distributed solver singleton per scalar type (reference ChASE_DIST, chase_c_interface.cpp:535-640).
+template <class T>
+struct Dist
+{
+    using R = chase::Base<T>;
+    std::unique_ptr<chase::Impl::pChASEGPU<T>> solver;
+    std::vector<T> vec;
+    std::vector<R> ritz;
+    T* V = nullptr;
+    R* ritzv = nullptr;
+    std::size_t N = 0, m_loc = 0;
+
+    static Dist& get()
+    {
+        static Dist s;
+        return s;
+    }
+    // mb/nb = 0: block layout (p?chase_init_), else block-cyclic (p?chase_init_blockcyclic_)
+    int init(int N_, int nev, int nex, long long mb, long long nb, T* H, int ldh, T* V_, R* ritzv_, int dim0, int dim1,
+             char grid_major, void* comm)
+    {
+        solver.reset();
+        try
+        {
+            if (comm == nullptr)
+                throw std::invalid_argument("communicator handle is NULL (create it with chase_b200_comm_init)");
+            auto* w = static_cast<chase::b200::WorldComm*>(comm);
+            const auto g = chase::b200::Grid2D::make(dim0, dim1, grid_major, w->rank, w->size);
+            const chase::b200::Dist1D dr((int64_t)N_, dim0, mb);
+            N = (std::size_t)N_;
+            m_loc = (std::size_t)dr.local_size(g.i);
+            V = V_;
+            if (V == nullptr)
+            {
+                vec.assign(std::max<std::size_t>(m_loc, 1) * (std::size_t)(nev + nex), T(0));
+                V = vec.data();
+            }
+            ritzv = ritzv_;
+            if (ritzv == nullptr)
+            {
+                ritz.assign((std::size_t)(nev + nex), R(0));
+                ritzv = ritz.data();
+            }
+            solver.reset(new chase::Impl::pChASEGPU<T>((std::size_t)N_, (std::size_t)nev, (std::size_t)nex, *w, dim0,
+                                                       dim1, grid_major, (std::size_t)mb, (std::size_t)nb, H,
+                                                       (std::size_t)ldh, V, std::max<std::size_t>(m_loc, 1), ritzv));
+        }
+        catch (const std::exception& e)
+        {
+            std::fprintf(stderr, "chase_b200: distributed init failed: %s\n", e.what());
+            g_last.error = e.what();
+            return 0;
+        }
+        return 1;
+    }
+    void finalize()
+    {
+        solver.reset();
+        std::vector<T>().swap(vec);
+        std::vector<R>().swap(ritz);
+    }
+    void solve(int deg, R tol, char mode, char opt, char qr)
+    {
+        if (solver)
+            run_solve<T>(solver.get(), N, deg, tol, mode, opt, qr, 1.0);
+    }
+    // local rows of the first nev eigenvectors (reference copy_first_nev_results, chase_c_interface.cpp:493-513)
+    void get_eigenpairs(T* out, int ld, R* ritz_out)
+    {
+        if (!solver || out == nullptr || ritz_out == nullptr || ld <= 0)
+            return;
+        const std::size_t nev = solver->GetNev();
+        const std::size_t ldv = std::max<std::size_t>(m_loc, 1);
+        for (std::size_t j = 0; j < nev; ++j)
+            std::memcpy(out + j * (std::size_t)ld, V + j * ldv, m_loc * sizeof(T));
+        std::memcpy(ritz_out, ritzv, nev * sizeof(R));
+    }
+    void get_resid(R* out)
+    {
+        if (!solver || !out)
+            return;
+        std::memcpy(out, solver->GetResid(), (solver->GetNev() + solver->GetNex()) * sizeof(R));
+    }
+};
+
 using SD = Seq<double>;
 using SS = Seq<float>;
 using SZ = Seq<std::complex<double>>;
 using SC = Seq<std::complex<float>>;
+using PD = Dist<double>;
+using PS = Dist<float>;
+using PZ = Dist<std::complex<double>>;
+using PC = Dist<std::complex<float>>;
 
 template <class F>
 void with_active_config(F&& f)
@@ -180,6 +279,14 @@ void with_active_config(F&& f)
         f(SZ::get().solver->GetConfig());
     else if (SC::get().solver)
         f(SC::get().solver->GetConfig());
+    else if (PD::get().solver)
+        f(PD::get().solver->GetConfig());
+    else if (PS::get().solver)
+        f(PS::get().solver->GetConfig());
+    else if (PZ::get().solver)
+        f(PZ::get().solver->GetConfig());
+    else if (PC::get().solver)
+        f(PC::get().solver->GetConfig());
 }
 
 size_t copy_out(const std::string& s, char* buf, size_t cap)
@@ -366,13 +473,174 @@ extern "C"
         }
     }
     void chase_has_cuda_(int* flag) { *flag = 1; }
-    void chase_has_nccl_(int* flag) { *flag = 0; }
+    void chase_has_nccl_(int* flag) { *flag = 1; }
     void chase_has_scalapack_(int* flag) { *flag = 0; }
     void chase_has_mpi_(int* flag) { *flag = 0; }
     void chase_print_config_(void)
     {
-        std::printf("%s: CUDA yes (hand-written sm_100a kernels, no cuBLAS/cuSOLVER), NCCL no, ScaLAPACK no, MPI no\n",
+        std::printf("%s: CUDA yes (hand-written sm_100a kernels, no cuBLAS/cuSOLVER), NCCL yes (bound at run time), ScaLAPACK no, MPI no\n",
                     chase_b200_version());
+    }
+
+    // ---- distributed entry points (reference chase_c_interface.h:61-195) ---------------------------------
+#define CB2_DIST_API(X, TT, CT, RT, SINGLETON)                                                                         \
+    void p##X##chase_init_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, CT* V, RT* ritzv, int* dim0,  \
+                           int* dim1, char* grid_major, MPI_Comm* comm, int* init)                                     \
+    {                                                                                                                  \
+        (void)m;                                                                                                       \
+        (void)n;                                                                                                       \
+        *init = SINGLETON::get().init(*N, *nev, *nex, 0, 0, reinterpret_cast<TT*>(H), *ldh, reinterpret_cast<TT*>(V), \
+                                      ritzv, *dim0, *dim1, *grid_major, comm ? *comm : nullptr);                       \
+    }                                                                                                                  \
+    void p##X##chase_init_internal_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, int* dim0, int* dim1,\
+                                    char* grid_major, MPI_Comm* comm, int* init)                                       \
+    {                                                                                                                  \
+        (void)m;                                                                                                       \
+        (void)n;                                                                                                       \
+        *init = SINGLETON::get().init(*N, *nev, *nex, 0, 0, reinterpret_cast<TT*>(H), *ldh, nullptr, nullptr, *dim0,  \
+                                      *dim1, *grid_major, comm ? *comm : nullptr);                                     \
+    }                                                                                                                  \
+    void p##X##chase_init_blockcyclic_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H, int* ldh, CT* V,  \
+                                       RT* ritzv, int* dim0, int* dim1, char* grid_major, int* irsrc, int* icsrc,      \
+                                       MPI_Comm* comm, int* init)                                                      \
+    {                                                                                                                  \
+        if ((irsrc && *irsrc != 0) || (icsrc && *icsrc != 0))                                                          \
+        {                                                                                                              \
+            std::fprintf(stderr, "chase_b200: block-cyclic source process must be 0 (as in the reference's numroc)\n"); \
+            *init = 0;                                                                                                 \
+            return;                                                                                                    \
+        }                                                                                                              \
+        *init = SINGLETON::get().init(*N, *nev, *nex, *mbsize, *nbsize, reinterpret_cast<TT*>(H), *ldh,               \
+                                      reinterpret_cast<TT*>(V), ritzv, *dim0, *dim1, *grid_major,                      \
+                                      comm ? *comm : nullptr);                                                         \
+    }                                                                                                                  \
+    void p##X##chase_init_blockcyclic_internal_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H, int* ldh, \
+                                                int* dim0, int* dim1, char* grid_major, int* irsrc, int* icsrc,        \
+                                                MPI_Comm* comm, int* init)                                             \
+    {                                                                                                                  \
+        (void)irsrc;                                                                                                   \
+        (void)icsrc;                                                                                                   \
+        *init = SINGLETON::get().init(*N, *nev, *nex, *mbsize, *nbsize, reinterpret_cast<TT*>(H), *ldh, nullptr,      \
+                                      nullptr, *dim0, *dim1, *grid_major, comm ? *comm : nullptr);                     \
+    }                                                                                                                  \
+    void p##X##chase_(int* deg, RT* tol, char* mode, char* opt, char* qr)                                              \
+    {                                                                                                                  \
+        SINGLETON::get().solve(*deg, *tol, *mode, *opt, *qr);                                                          \
+    }                                                                                                                  \
+    void p##X##chase_finalize_(int* flag)                                                                              \
+    {                                                                                                                  \
+        SINGLETON::get().finalize();                                                                                   \
+        *flag = 0;                                                                                                     \
+    }                                                                                                                  \
+    void p##X##chase_get_eigenpairs_(CT* V, int* ld, RT* ritzv)                                                        \
+    {                                                                                                                  \
+        if (ld)                                                                                                        \
+            SINGLETON::get().get_eigenpairs(reinterpret_cast<TT*>(V), *ld, ritzv);                                     \
+    }                                                                                                                  \
+    void p##X##chase_get_resid_(RT* r) { SINGLETON::get().get_resid(r); }
+
+    CB2_DIST_API(d, double, double, double, PD)
+    CB2_DIST_API(s, float, float, float, PS)
+    CB2_DIST_API(z, cd, CHASE_B200_CD, double, PZ)
+    CB2_DIST_API(c, cf, CHASE_B200_CF, float, PC)
+#undef CB2_DIST_API
+
+    // ---- communicator bootstrap (include/chase_b200_comm.h) ------------------------------------------------
+    int chase_b200_comm_unique_id(void* id_out)
+    {
+        try
+        {
+            static_assert(sizeof(ncclUniqueId) == CHASE_B200_COMM_ID_BYTES, "ncclUniqueId size");
+            ncclUniqueId id;
+            if (chase::b200::NcclApi::get().GetUniqueId(&id) != ncclSuccess)
+                return -1;
+            std::memcpy(id_out, &id, sizeof id);
+            return 0;
+        }
+        catch (const std::exception& e)
+        {
+            std::fprintf(stderr, "%s\n", e.what());
+            return -1;
+        }
+    }
+    int chase_b200_comm_init(int rank, int nranks, const void* id_in, int device, void** comm_out)
+    {
+        try
+        {
+            if (cudaSetDevice(device) != cudaSuccess)
+            {
+                std::fprintf(stderr, "chase_b200: cudaSetDevice(%d) failed\n", device);
+                return -1;
+            }
+            ncclUniqueId id;
+            std::memcpy(&id, id_in, sizeof id);
+            auto* w = new chase::b200::WorldComm;
+            w->rank = rank;
+            w->size = nranks;
+            w->device = device;
+            ncclResult_t r = chase::b200::NcclApi::get().CommInitRank(&w->comm, nranks, id, rank);
+            if (r != ncclSuccess)
+            {
+                std::fprintf(stderr, "chase_b200: ncclCommInitRank failed: %s\n",
+                             chase::b200::NcclApi::get().GetErrorString(r));
+                delete w;
+                return -1;
+            }
+            *comm_out = w;
+            return 0;
+        }
+        catch (const std::exception& e)
+        {
+            std::fprintf(stderr, "%s\n", e.what());
+            return -1;
+        }
+    }
+    int chase_b200_comm_free(void* comm)
+    {
+        auto* w = static_cast<chase::b200::WorldComm*>(comm);
+        if (!w)
+            return 0;
+        if (w->comm)
+            chase::b200::NcclApi::get().CommDestroy(w->comm);
+        delete w;
+        return 0;
+    }
+    int chase_b200_comm_rank(void* comm) { return comm ? static_cast<chase::b200::WorldComm*>(comm)->rank : -1; }
+    int chase_b200_comm_size(void* comm) { return comm ? static_cast<chase::b200::WorldComm*>(comm)->size : -1; }
+    long long chase_b200_local_size(long long N, int nprocs, long long nb, int p)
+    {
+        return chase::b200::Dist1D(N, nprocs, nb).local_size(p);
+    }
+    int chase_b200_global_indices(long long N, int nprocs, long long nb, int p, long long* out)
+    {
+        const auto g = chase::b200::Dist1D(N, nprocs, nb).global_indices(p);
+        for (std::size_t i = 0; i < g.size(); ++i)
+            out[i] = g[i];
+        return 0;
+    }
+    int chase_b200_redistribution_map(long long N, int src_nprocs, long long src_nb, long long src_stride,
+                                      int dst_nprocs, long long dst_nb, int pd, long long* out)
+    {
+        const chase::b200::Dist1D src(N, src_nprocs, src_nb), dst(N, dst_nprocs, dst_nb);
+        for (const auto& c : chase::b200::redistribution_list(src, src_stride, dst, pd))
+            for (long long t = 0; t < c.len; ++t)
+                out[c.dst0 + t] = c.src0 + t;
+        return 0;
+    }
+    int chase_b200_grid_coords(int dim0, int dim1, char grid_major, int rank, int* row_out, int* col_out)
+    {
+        try
+        {
+            const auto g = chase::b200::Grid2D::make(dim0, dim1, grid_major, rank, dim0 * dim1);
+            *row_out = g.i;
+            *col_out = g.j;
+            return 0;
+        }
+        catch (const std::exception& e)
+        {
+            std::fprintf(stderr, "chase_b200: %s\n", e.what());
+            return -1;
+        }
     }
 
     void chase_b200_start_vectors_d(int64_t N, int64_t m, double* V, int64_t ldv)

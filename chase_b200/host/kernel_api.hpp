@@ -20,6 +20,11 @@ struct K;
     {                                                                                                                  \
         static constexpr auto gemm = chase_b200_gemm_##X;                                                              \
         static constexpr auto hemm = chase_b200_hemm_##X;                                                              \
+        static constexpr auto hemm_rect = chase_b200_hemm_rect_##X;                                                    \
+        static constexpr auto gather_rows = chase_b200_gather_rows_##X;                                                \
+        static constexpr auto axpy_cols = chase_b200_axpy_cols_##X;                                                    \
+        static constexpr auto shift_diag_list = chase_b200_shift_diag_list_##X;                                        \
+        static constexpr auto rng_normal_rows = chase_b200_rng_normal_rows_##X;                                        \
         static constexpr auto potrf = chase_b200_potrf_##X;                                                            \
         static constexpr auto trsm = chase_b200_trsm_##X;                                                              \
         static constexpr auto shift_abstrace = chase_b200_shift_abstrace_##X;                                          \

@@ -74,6 +74,16 @@ def hemm(n, k, alpha, A, lda, B, ldb, beta, C, ldc, shift=0.0, theta=None):
                   _stream()), "hemm")
 
 
+def hemm_rect(ta, M, K, k, alpha, A, lda, B, ldb, beta, C, ldc):
+    """C(M x k) <- alpha op(A) B(K x k) + beta C; op(A) = A (M x K) or A^H (A stored K x M) for ta."""
+    f = getattr(lib(), f"chase_b200_hemm_rect_{_sfx(C)}")
+    ar, ai = _c(alpha)
+    br, bi = _c(beta)
+    return _chk(f(int(ta), ctypes.c_int64(M), ctypes.c_int64(K), ctypes.c_int64(k), ar, ai, _ptr(A),
+                  ctypes.c_int64(lda), _ptr(B), ctypes.c_int64(ldb), br, bi, _ptr(C), ctypes.c_int64(ldc),
+                  _stream()), "hemm_rect")
+
+
 def potrf(n, G, ldg, info):
     f = getattr(lib(), f"chase_b200_potrf_{_sfx(G)}")
     return _chk(f(ctypes.c_int64(n), _ptr(G), ctypes.c_int64(ldg), _ptr(info), _stream()), "potrf")

@@ -42,6 +42,13 @@ extern "C"
     int chase_b200_hemm_##X(int64_t n, int64_t k, double alpha_re, double alpha_im, const void* A, int64_t lda,       \
                             const void* B, int64_t ldb, double beta_re, double beta_im, void* C, int64_t ldc,         \
                             double shift, const double* theta, void* stream);                                         \
+    /* Distributed filter step on a local block: C(M x k) <- alpha op(A) B(K x k) + beta C, op(A) = A (stored M x K)  \
+       for ta == 0 or A^H (stored K x M) for ta == 1.  Same TMA + DMMA kernel as chase_b200_hemm.  Replaces the two   \
+       cublasTgemm of cuda_nccl::MatrixMultiplyMultiVectors (reference linalg/internal/nccl/hemm.hpp:325-332,         \
+       382-389). */                                                                                                    \
+    int chase_b200_hemm_rect_##X(int ta, int64_t M, int64_t K, int64_t k, double alpha_re, double alpha_im,           \
+                                 const void* A, int64_t lda, const void* B, int64_t ldb, double beta_re,              \
+                                 double beta_im, void* C, int64_t ldc, void* stream);                                 \
     /* Upper Cholesky G = R^H R in place (strict lower part untouched). *info_dev (device int, must be zeroed by      \
        the caller) receives the 1-based index of the first non-positive pivot, LAPACK ?potrf convention.              \
        Replaces cusolverDnTpotrf (reference cuda/cholqr.hpp:119-125). */                                              \
@@ -72,6 +79,24 @@ extern "C"
        the reference's per-call cublasTswap (Impl/chase_gpu/chase_gpu.hpp:1000-1006). */                              \
     int chase_b200_gather_cols_##X(int64_t rows, int cnt, const int* scols_dev, const int* dcols_dev,                 \
                                    const void* src, int64_t lds, void* dst, int64_t ldd, void* stream);               \
+    /* dst[i, :] <- src[src_row[i], :] for every i < rows with src_row[i] >= 0 (device int64 map).  piece_stride > 0: \
+       src is an all-gathered stack of (lds x cols) panels piece_stride elements apart and src_row = piece * lds +     \
+       row.  The one layout primitive of the distributed backend; replaces the broadcast loops of redistributeImpl    \
+       (reference linalg/distMatrix/distMultiVector.hpp:2817-2909). */                                                \
+    int chase_b200_gather_rows_##X(int64_t rows, int64_t cols, const int64_t* src_row_dev, const void* src,           \
+                                   int64_t lds, int64_t piece_stride, void* dst, int64_t ldd, void* stream);          \
+    /* C[:, j] += g * gvec[j] * E[:, j] (gvec: device, cols doubles).  With g = -1, gvec = theta it turns A V into    \
+       the residual block A V - V Theta (reference cuda/residuals.cu:113-251 does the subtraction inside its norm     \
+       kernel). */                                                                                                     \
+    int chase_b200_axpy_cols_##X(int64_t rows, int64_t cols, const double* gvec_dev, double g_re, double g_im,        \
+                                 const void* E, int64_t lde, void* Cm, int64_t ldc, void* stream);                    \
+    /* A[lin[t]] += c, t < cnt: local copies of global diagonal entries (reference chase_shift_mgpu_matrix,           \
+       cuda/shiftDiagonal.cu:100-150). */                                                                              \
+    int chase_b200_shift_diag_list_##X(int64_t cnt, const int64_t* lin_dev, void* A, double c, void* stream);         \
+    /* Philox N(0,1) fill addressed by global element index grow[i] + j * nglobal (layout-independent start block;   \
+       the reference seeds cuRAND per grid row instead, Impl/pchase_gpu/pchase_gpu.hpp:652-688). */                   \
+    int chase_b200_rng_normal_rows_##X(int64_t rows, int64_t cols, const int64_t* grow_dev, int64_t nglobal,          \
+                                       void* Xm, int64_t ldx, uint64_t seed, void* stream);                           \
     /* Y[:, v] <- A^H X[:, v], v < nv (A is rows x cols).  HBM-bound Lanczos product; replaces the 4-column           \
        cublasTgemm(OP_C) of cuda::lanczos (reference linalg/internal/cuda/lanczos.hpp:178-186). */                    \
     int chase_b200_gemv_conjt_##X(int64_t rows, int64_t cols, const void* A, int64_t lda, const void* Xm,             \

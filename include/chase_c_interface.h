@@ -27,6 +27,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "mpi_shim.h" /* MPI_Comm for MPI-less builds; include <mpi.h> first to use the real one */
+
 #ifdef __cplusplus
 extern "C"
 {
@@ -85,6 +87,32 @@ extern "C"
     void chase_has_scalapack_(int* flag);
     void chase_has_mpi_(int* flag);
     void chase_print_config_(void);
+
+    /* ---- distributed (multi-GPU) entry points: reference interface/chase_c_interface.h:61-195 -------------------
+       One process per GPU on a dim0 x dim1 grid (dim0 >= dim1; grid_major 'R' | 'C' gives the rank order of
+       MPI_Cart_create, grid/mpiGrid2D.hpp:402-430).  H / V are the LOCAL pieces: H is m x n with
+       m = local rows, n = local columns of the block layout (distMatrix.hpp:1992-2039) or of the block-cyclic layout
+       (numroc, distMatrix.hpp:44-67; irsrc = icsrc = 0); V holds the m local rows of the nev+nex vectors (ld = m).
+       *comm is the handle made by chase_b200_comm_init (include/chase_b200_comm.h). */
+#define CHASE_B200_DIST_API(X, CT, RT)                                                                                 \
+    void p##X##chase_init_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, CT* V, RT* ritzv, int* dim0,  \
+                           int* dim1, char* grid_major, MPI_Comm* comm, int* init);                                    \
+    void p##X##chase_init_internal_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, int* dim0, int* dim1,\
+                                    char* grid_major, MPI_Comm* comm, int* init);                                      \
+    void p##X##chase_init_blockcyclic_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H, int* ldh, CT* V,  \
+                                       RT* ritzv, int* dim0, int* dim1, char* grid_major, int* irsrc, int* icsrc,      \
+                                       MPI_Comm* comm, int* init);                                                     \
+    void p##X##chase_init_blockcyclic_internal_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H, int* ldh, \
+                                                int* dim0, int* dim1, char* grid_major, int* irsrc, int* icsrc,        \
+                                                MPI_Comm* comm, int* init);                                            \
+    void p##X##chase_(int* deg, RT* tol, char* mode, char* opt, char* qr);                                             \
+    void p##X##chase_finalize_(int* flag);                                                                             \
+    void p##X##chase_get_eigenpairs_(CT* V, int* ld, RT* ritzv);                                                       \
+    void p##X##chase_get_resid_(RT* resid);
+    CHASE_B200_DIST_API(d, double, double)
+    CHASE_B200_DIST_API(s, float, float)
+    CHASE_B200_DIST_API(z, CHASE_B200_CD, double)
+    CHASE_B200_DIST_API(c, CHASE_B200_CF, float)
 
     /* ---- chase_b200 additions (introspection for parity tests and benchmarks) ---- */
     /* residuals of the last solve (nev+nex values, ordered like ritzv) */

@@ -1,0 +1,107 @@
+"""Multi-rank parity check of the distributed backend (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/dist_check.py [--grid 2x2] [--layout block|cyclic] [--case c1_clement_d_N1001] ...
+
+Every rank builds the (small) global matrix, keeps its local block, solves through p?chase_init_[blockcyclic_] /
+p?chase_, and the gathered result is compared with the golden trace of the UNMODIFIED reference CPU solver
+(tests/golden/*.json): because the start block is the reference's global mt19937 stream regardless of the layout, the
+distributed solve must take the same decisions (iterations, filtered vectors, HEMM schedule, locks) and deliver the
+same eigenvalues (1e-10 relative) as the serial reference."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from chase_b200 import dist as cd  # noqa: E402
+from oracle import chase_oracle as co  # noqa: E402  (checker only)
+from tests.golden_util import DT, load, parse_trace  # noqa: E402
+
+
+def run_case(world, name, grid, layout, major):
+    import torch.distributed as dist
+
+    g = load(name)
+    p = g["problems"][0]
+    dt = DT[g["type"]]
+    N, nev, nex = g["N"], g["nev"], g["nex"]
+    H = co.clement(N, dt) if g["matrix"] == "clement" else co.uniform_diag(N, dt)
+    nb = 0 if layout == "block" else 32
+    r, c = grid
+    i, j = cd.grid_coords(r, c, major, world.rank)
+    gr, gc = cd.global_indices(N, r, nb, i), cd.global_indices(N, c, nb, j)
+    Hloc = np.asfortranarray(H[np.ix_(gr, gc)])
+    with cd.PChASE(world, N, nev, nex, Hloc, grid=grid, major=major, mb=nb, nb=nb) as s:
+        res = s.solve(deg=g["deg"], tol=g["tol"], opt="S" if g["opt"] else "N", trace=True)
+    ref, got = parse_trace(p["trace"]), parse_trace(res.trace)
+    fails = []
+    if res.iterations != p["iterations"]:
+        fails.append(f"iterations {res.iterations} != {p['iterations']}")
+    if res.filtered_vecs != p["filtered_vecs"]:
+        fails.append(f"filtered_vecs {res.filtered_vecs} != {p['filtered_vecs']}")
+    if [(b, o) for (b, o, _, _) in got["hemm"]] != [(b, o) for (b, o, _, _) in ref["hemm"]]:
+        fails.append("HEMM schedule differs")
+    if got["locks"] != ref["locks"]:
+        fails.append(f"locks {got['locks']} != {ref['locks']}")
+    refv = np.array(p["ritzv"][:nev])
+    rel = float(np.max(np.abs(res.ritzv[:nev] - refv) / np.abs(refv)))
+    if rel > 1e-10:
+        fails.append(f"eigenvalues off by {rel:.2e}")
+    if not np.all(res.resid[:nev] < 100 * g["tol"]):
+        fails.append("residuals above tolerance")
+    # assemble the eigenvectors (column layout: rows split over grid rows, replicated over grid columns)
+    parts = [None] * world.size
+    if world.size > 1:
+        dist.all_gather_object(parts, (i, j, gr, res.V[:len(gr), :nev]))
+    else:
+        parts = [(i, j, gr, res.V[:len(gr), :nev])]
+    V = np.zeros((N, nev), dtype=dt)
+    for (pi, pj, rows, blk) in parts:
+        if pj == 0:
+            V[rows, :] = blk
+    rr = np.linalg.norm(H @ V - V * res.ritzv[:nev], axis=0)
+    if not (np.all(rr < 1e-8) and np.all(rr > 0)):
+        fails.append(f"recomputed residual max {rr.max():.2e}")
+    orth = float(np.linalg.norm(V.conj().T @ V - np.eye(nev)))
+    if orth > 1e-9:
+        fails.append(f"orthogonality {orth:.2e}")
+    # replicas over grid columns must agree
+    for (pi, pj, rows, blk) in parts:
+        if pj != 0 and np.max(np.abs(V[rows, :] - blk)) > 1e-12:
+            fails.append("column-layout replicas differ")
+    return dict(case=name, grid=f"{r}x{c}", layout=layout, major=major, iterations=res.iterations,
+                filtered_vecs=res.filtered_vecs, max_rel_eig=rel, max_resid=float(rr.max()), orth=orth, fails=fails)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="serial_clement_d_N256,serial_clement_z_N256,c1_clement_d_N1001,c2s_uniform_d_N2000")
+    ap.add_argument("--grid", default="")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    world = cd.World()
+    grids = [tuple(int(x) for x in a.grid.split("x"))] if a.grid else [cd.grid_dims(world.size)]
+    if not a.grid and world.size in (2, 4, 8):
+        grids.append((world.size, 1))
+    results, bad = [], 0
+    for name in a.cases.split(","):
+        for grid in grids:
+            for layout, major in (("block", "R"), ("cyclic", "C")):
+                r = run_case(world, name, grid, layout, major)
+                results.append(r)
+                bad += len(r["fails"])
+                if world.rank == 0:
+                    print(("FAIL " if r["fails"] else "ok   ") + json.dumps(r), flush=True)
+    if world.rank == 0 and a.out:
+        json.dump(results, open(a.out, "w"), indent=1)
+    world.close()
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,30 @@ def test_hemm_residual_block_and_norms(t):
     assert np.max(np.abs(out.cpu().numpy() - ref) / ref) < TOL[t] * 10
 
 
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("ta", [0, 1])
+@pytest.mark.parametrize("M,Kd,kcols", [(640, 512, 96), (515, 1001, 37), (1001, 300, 130), (96, 64, 5)])
+def test_hemm_rect_local_block(t, ta, M, Kd, kcols):
+    """Distributed filter step on a rectangular local block: C <- alpha op(A) B + beta C with op = N or ^H
+    (reference nccl/hemm.hpp:325-332, 382-389: cublasTgemm(OP_C | OP_N) on the local block)."""
+    k = K()
+    rng = np.random.default_rng(M + 7 * Kd + ta)
+    A = rnd(rng, (Kd, M) if ta else (M, Kd), t)  # stored shape
+    B = rnd(rng, (Kd, kcols), t)
+    C = rnd(rng, (M, kcols), t)
+    alpha, beta = 0.37, -1.25
+    wide = np.complex128 if t in "cz" else np.float64
+    opA = A.astype(wide).conj().T if ta else A.astype(wide)
+    ref = alpha * (opA @ B.astype(wide)) + beta * C.astype(wide)
+    lda = (A.shape[0] + 15) // 16 * 16
+    ldb = (Kd + 15) // 16 * 16
+    ldc = (M + 15) // 16 * 16
+    dA, dB, dC = k.colmajor(A, lda), k.colmajor(B, ldb), k.colmajor(C, ldc)
+    k.hemm_rect(ta, M, Kd, kcols, alpha, dA, lda, dB, ldb, beta, dC, ldc)
+    torch.cuda.synchronize()
+    assert relerr(k.to_numpy(dC, M), ref) < TOL[t]
+
+
 def _fixture(name):
     p = os.path.join(os.path.dirname(__file__), "golden", "qr_fixtures", name)
     return p if os.path.exists(p) else None
