@@ -86,7 +86,7 @@ def main():
     a = ap.parse_args()
     world = cd.World()
     grids = [tuple(int(x) for x in a.grid.split("x"))] if a.grid else [cd.grid_dims(world.size)]
-    if not a.grid and world.size in (2, 4, 8):
+    if not a.grid and world.size in (4, 8):
         grids.append((world.size, 1))
     results, bad = [], 0
     for name in a.cases.split(","):
@@ -100,6 +100,10 @@ def main():
     if world.rank == 0 and a.out:
         json.dump(results, open(a.out, "w"), indent=1)
     world.close()
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        dist.destroy_process_group()
     sys.exit(1 if bad else 0)
 
 
