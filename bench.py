@@ -107,7 +107,7 @@ def ref_sample_shape(workload, cores, override=0):
         n = override
     else:
         # ~10-30 s of CPU work: filter FLOPs grow like N^3 at fixed nev/N (971 GFLOP at N=4000, real double)
-        n = 4000 if cores <= 16 else (6000 if cores <= 64 else 8000)
+        n = 4000 if cores <= 8 else (6000 if cores <= 32 else 8000)
         if t == "z":
             n = n * 5 // 8
     n = min(n, N)
@@ -293,7 +293,8 @@ def ours(a):
                "h2d_bytes_per_step": N * N * es + N * m * es, "d2h_bytes_per_step": N * m * es + 2 * m * 8,
                "time_to_solution_s": secs2 / a.steps, "iterations": rs2[-1].iterations,
                "filtered_vecs": rs2[-1].filtered_vecs,
-               "start_vectors": "reference CPU stream (mt19937(1337)+normal on the host, uploaded)"}
+               "start_vectors": "reference CPU stream (mt19937(1337)+normal; generated on the host at the first solve, "
+                                "kept on the device afterwards)"}
     solver.finalize()
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------------

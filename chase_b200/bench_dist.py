@@ -1,0 +1,197 @@
+"""Multi-GPU arm of bench.py (one rank per GPU under torchrun).
+
+Weak scaling of BASELINE config C2 over an r x c grid (1x1, 2x1, 2x2, 4x2): nev = 1000, nex = 400 fixed, N grows like
+sqrt(#GPUs) so that every GPU keeps a 3.2 GB block of A and the same filter work per call
+(N = 20000, 28288, 40000, 56576), block-cyclic layout with 64 x 64 blocks as in the reference's examples
+(examples/1_hello_world/1_hello_world.cpp:102).  The matrix is the same dense uniform-spectrum generator as the
+single-GPU arm, A = Q diag(lambda) Q^T with 3 Householder reflectors, written as diag + 9 rank-one terms so that every
+rank builds its own block on its own GPU without ever holding N^2 numbers.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+
+import numpy as np
+
+BASE = ("d", 20000, 1000, 400)
+
+
+def weak_n(gpus: int) -> int:
+    return int(round(BASE[1] * np.sqrt(gpus) / 64.0)) * 64
+
+
+def lowrank_terms(N: int, cplx: bool):
+    """A = diag(lam) + sum_t coef[t] * X[:, t] Y[:, t]^H, identical to bench.make_matrix / oracle.dense_from_spectrum
+    before its final symmetrisation."""
+    lam = 100.0 * (1e-4 + np.arange(N) * (1.0 - 1e-4) / N)
+    rng = np.random.default_rng(7)
+    X, Y, coef = [], [], []
+
+    def apply(v):
+        w = lam * v
+        for x, y, c in zip(X, Y, coef):
+            w = w + c * x * np.vdot(y, v)
+        return w
+
+    for _ in range(3):
+        v = rng.standard_normal(N)
+        if cplx:
+            v = v + 1j * rng.standard_normal(N)
+        v = v / np.linalg.norm(v)
+        w = apply(v)
+        s = np.vdot(v, w)
+        X += [v, w, v]
+        Y += [w, v, v]
+        coef += [-2.0, -2.0, 4.0 * s]
+    return lam, np.stack(X, 1), np.stack(Y, 1), np.array(coef)
+
+
+def local_block(N, gr, gc, cplx, device):
+    import torch
+
+    lam, X, Y, coef = lowrank_terms(N, cplx)
+    dt = torch.complex128 if cplx else torch.float64
+    Xl = torch.from_numpy(X[gr, :] * coef[None, :]).to(device).to(dt)
+    Yl = torch.from_numpy(Y[gc, :]).to(device).to(dt)
+    A = Xl @ Yl.conj().T  # m_loc x n_loc
+    # global diagonal entries inside this block
+    pos = {int(g): k for k, g in enumerate(gc)}
+    rows = [k for k, g in enumerate(gr) if int(g) in pos]
+    cols = [pos[int(gr[k])] for k in rows]
+    if rows:
+        A[rows, cols] += torch.from_numpy(lam[gr[rows]]).to(device).to(dt)
+    return A, lam
+
+
+def run(a):
+    import torch
+    import torch.distributed as tdist
+
+    import chase_b200
+    from chase_b200 import dist as cd
+
+    if "WORLD_SIZE" not in os.environ or int(os.environ["WORLD_SIZE"]) != a.gpus:
+        # started without the launcher: re-launch ourselves the way the driver does
+        import subprocess
+        import sys
+
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533"] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
+
+    from bench import Clocks, run_reference_cpu, sample_text  # noqa: E402 (bench.py is on sys.path)
+
+    L = chase_b200.lib()
+    world = cd.World()
+    rank, G = world.rank, world.size
+    t, _, nev, nex = BASE
+    N = weak_n(G)
+    m = nev + nex
+    r, c = cd.grid_dims(G)
+    nb = 64
+    i, j = cd.grid_coords(r, c, "R", rank)
+    gr, gc = cd.global_indices(N, r, nb, i), cd.global_indices(N, c, nb, j)
+    dev = f"cuda:{world.device}"
+    A, lam = local_block(N, gr, gc, False, dev)
+    Hh = torch.empty((len(gc), len(gr)), dtype=A.dtype, pin_memory=True)  # column-major m_loc x n_loc
+    Hh.copy_(A.T.contiguous())
+    del A
+    torch.cuda.empty_cache()
+    Vh = torch.zeros((m, max(len(gr), 1)), dtype=Hh.dtype, pin_memory=True)
+    H, V = Hh.numpy().T, Vh.numpy().T
+
+    peak = max(L.chase_b200_dmma_peak(40000, None) for _ in range(3)) / 1e12
+
+    def flag(name, v):
+        getattr(L, name)(ctypes.byref(ctypes.c_int(v)))
+
+    solver = cd.PChASE(world, N, nev, nex, H, grid=(r, c), major="R", mb=nb, nb=nb, V_loc=V)
+    tol = 1e-10
+
+    def check(res):
+        rel = float(np.max(np.abs(res.ritzv[:nev] - lam[:nev]) / lam[:nev]))
+        assert rel < 1e-10, f"eigenvalues off: {rel}"
+        assert float(res.resid[:nev].max()) < 100 * tol
+        return rel
+
+    def sync():
+        torch.cuda.synchronize()
+        L.chase_b200_device_sync()
+        world.barrier()
+
+    def timed(nsteps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.chase_b200_launch_count()
+        e0.record()
+        rs = [solver.solve(deg=20, tol=tol, copy=False) for _ in range(nsteps)]
+        e1.record()
+        sync()
+        return rs, world.max(e0.elapsed_time(e1) * 1e-3), L.chase_b200_launch_count() - l0
+
+    # ---- value: local blocks resident in HBM, device RNG ----------------------------------------------------
+    flag("chase_b200_set_device_rng_", 1)
+    flag("chase_b200_set_matrix_resident_", 0)
+    solver.solve(deg=20, tol=tol, copy=False)
+    flag("chase_b200_set_matrix_resident_", 1)
+    for _ in range(max(a.warmup - 1, 0)):
+        solver.solve(deg=20, tol=tol, copy=False)
+    L.chase_b200_hemm_profile_enable(1)
+    ck = Clocks(world.device)
+    if rank == 0:
+        ck.start()
+    rs, secs, launches = timed(a.steps)
+    clocks = ck.stop() if rank == 0 else None
+    hp = (ctypes.c_double * 4)()
+    L.chase_b200_hemm_profile_read(hp)
+    L.chase_b200_hemm_profile_enable(0)
+    rel = max(check(x) for x in rs)
+    flop_filter = sum(x.stats["gflop_filter"] for x in rs) * 1e9  # whole job (global N)
+    value = flop_filter / secs / 1e12
+    st = rs[-1].stats
+    kern_tf = hp[2] / (hp[1] * 1e-3) / 1e12 if hp[1] > 0 else 0.0
+    kern_tf_min = -world.max(-kern_tf)
+
+    # ---- e2e: host buffers through p?chase_ ---------------------------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        flag("chase_b200_set_device_rng_", 0)
+        flag("chase_b200_set_matrix_resident_", 0)
+        solver.solve(deg=20, tol=tol, copy=False)
+        rs2, secs2, _ = timed(a.steps)
+        rel = max(rel, max(check(x) for x in rs2))
+        es = H.itemsize
+        e2e = {"value": sum(x.stats["gflop_filter"] for x in rs2) * 1e9 / secs2 / 1e12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": (N * N * es) + G * len(gr) * m * es,
+               "d2h_bytes_per_step": G * (len(gr) * m * es + 2 * m * 8), "time_to_solution_s": secs2 / a.steps,
+               "iterations": rs2[-1].iterations, "filtered_vecs": rs2[-1].filtered_vecs,
+               "start_vectors": "reference CPU stream (mt19937(1337)+normal; rows of this grid row generated on the host at "
+                                "the first solve, kept on the device afterwards)"}
+    solver.finalize()
+
+    if rank == 0:
+        roofline = {"bound": "tensor", "kernel": "hemm_tma_kernel (FP64 DMMA, TMA-fed; local A and A^H blocks)",
+                    "achieved": kern_tf, "peak": peak, "unit": "TFLOP/s", "frac": kern_tf / peak, "traffic": None,
+                    "peak_source": "measured live per GPU: register-resident DMMA.8x8x4 loop (chase_b200_dmma_peak)",
+                    "launches": int(hp[0]), "kernel_ms_total": hp[1], "kernel_share_of_step": hp[1] * 1e-3 / secs,
+                    "achieved_min_over_ranks": kern_tf_min, "per": "GPU (rank 0)"}
+        line = {
+            "metric": "filter_hemm_tflops_per_time_to_solution", "value": value, "unit": "TFLOP/s", "n_gpus": G,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"c2 weak-scaled: d N={N} nev={nev} nex={nex} uniform spectrum, dense Q diag Q^H, "
+                                   f"tol 1e-10 deg 20 opt; {r}x{c} grid, block-cyclic {nb}x{nb}, NCCL",
+                       "l2": "inputs larger than L2 (local A block is %.1f GB)" % (len(gr) * len(gc) * H.itemsize / 1e9),
+                       "start_vectors": "device Philox RNG (value) / reference CPU stream (e2e)"},
+            "time_to_solution_s": secs / a.steps, "iterations": rs[-1].iterations, "filtered_vecs": rs[-1].filtered_vecs,
+            "filter_phase_tflops": st["gflop_filter"] / st["t_filter"] / 1e3 if st["t_filter"] > 0 else None,
+            "phases_s": {k[2:]: st[k] for k in ("t_all", "t_initvecs", "t_lanczos", "t_filter", "t_qr", "t_rr", "t_resid")},
+            "max_rel_eig_err": rel, "gpu_launches": int(launches), "gpu_launches_per": "rank 0", "clocks": clocks,
+            "roofline": roofline, "e2e": e2e,
+        }
+        print(json.dumps(line), flush=True)
+    world.close()
+    if tdist.is_initialized():
+        tdist.destroy_process_group()

@@ -134,6 +134,11 @@ public:
         {
             CB2_KCHECK(KK::rng_normal((int64_t)N_, (int64_t)nevex_, dV1_, (int64_t)ld_, 24141ull, stream_));
         }
+        else if (random && dV0_ != nullptr)
+        {
+            // the reference stream is a pure function of (N, nev+nex, T): generated once, then kept on the device
+            CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nevex_, dV0_, (int64_t)ld_, dV1_, (int64_t)ld_, stream_));
+        }
         else
         {
             if (random)
@@ -142,6 +147,11 @@ public:
             }
             CB2_CHECK(cudaMemcpy2DAsync(dV1_, ld_ * sizeof(T), V_, ldv_ * sizeof(T), N_ * sizeof(T), nevex_,
                                         cudaMemcpyHostToDevice, stream_));
+            if (random)
+            {
+                dV0_ = alloc<T>(ld_ * nevex_);
+                CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nevex_, dV1_, (int64_t)ld_, dV0_, (int64_t)ld_, stream_));
+            }
         }
         CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nevex_, dV1_, (int64_t)ld_, dV2_, (int64_t)ld_, stream_));
         // the host matrix is (re-)read at every solve: callers fill or perturb H
@@ -573,6 +583,7 @@ private:
     cudaStream_t stream_ = nullptr;
     std::size_t ld_ = 0, ldg_ = 0;
     T *dH_ = nullptr, *dV1_ = nullptr, *dV2_ = nullptr, *dW_ = nullptr, *dG_ = nullptr, *dZ_ = nullptr;
+    T* dV0_ = nullptr; // device copy of the reference start block (parity mode), filled at the first random solve
     unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr;
     std::size_t heev_ws_bytes_ = 0, trsm_ws_bytes_ = 0, splitk_ws_bytes_ = 0;
     double *dTheta_ = nullptr, *dNorms_ = nullptr;

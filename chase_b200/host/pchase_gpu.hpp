@@ -118,6 +118,11 @@ public:
             CB2_KCHECK(KK::rng_normal_rows((int64_t)m_loc_, (int64_t)nevex_, map_full2v_, (int64_t)N_, dV1_,
                                            (int64_t)ldv_, 24141ull, stream_));
         }
+        else if (random && dV0_ != nullptr)
+        {
+            // the reference stream is a pure function of (N, nev+nex, T): generated once, then kept on the device
+            CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)nevex_, dV0_, (int64_t)ldv_, dV1_, (int64_t)ldv_, stream_));
+        }
         else
         {
             if (random)
@@ -142,6 +147,11 @@ public:
             if (m_loc_ > 0)
                 CB2_CHECK(cudaMemcpy2DAsync(dV1_, ldv_ * sizeof(T), V_, ldvh_ * sizeof(T), m_loc_ * sizeof(T), nevex_,
                                             cudaMemcpyHostToDevice, stream_));
+            if (random)
+            {
+                dV0_ = alloc<T>(ldv_ * nevex_);
+                CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)nevex_, dV1_, (int64_t)ldv_, dV0_, (int64_t)ldv_, stream_));
+            }
         }
         CB2_KCHECK(KK::lacpy((int64_t)ldv_, (int64_t)nevex_, dV1_, (int64_t)ldv_, dV2_, (int64_t)ldv_, stream_));
         if (!(keep_device_matrix_ && matrix_on_device_) && m_loc_ > 0 && n_loc_ > 0)
@@ -746,6 +756,7 @@ private:
     T *dH_ = nullptr, *dV1_ = nullptr, *dV2_ = nullptr, *dVs_ = nullptr, *dGath_ = nullptr, *dG_ = nullptr,
       *dZ_ = nullptr;
     T* dW_[4] = {nullptr, nullptr, nullptr, nullptr};
+    T* dV0_ = nullptr; // device copy of this rank's rows of the reference start block (parity mode)
     unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr;
     std::size_t heev_ws_bytes_ = 0, trsm_ws_bytes_ = 0, splitk_ws_bytes_ = 0;
     double *dTheta_ = nullptr, *dNorms_ = nullptr;
