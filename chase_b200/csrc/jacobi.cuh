@@ -253,12 +253,13 @@ __global__ void jacobi_diag_kernel(int n, const C* Gw, double* w)
 
 // Z[:, j] <- Zw[:, perm[j]]  (narrowed to the storage type)
 template <class T>
-__global__ void jacobi_gather_kernel(int n, const typename Traits<T>::comp* Zw, const int* perm, T* Z, long long ldz)
+__global__ void jacobi_gather_kernel(int n, const typename Traits<T>::comp* Zw, long long ldzw, const int* perm, T* Z,
+                                     long long ldz)
 {
     const int j = blockIdx.y;
     const int src = perm[j];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        Z[i + j * ldz] = narrow<T>(Zw[i + (long long)src * n]);
+        Z[i + j * ldz] = narrow<T>(Zw[i + (long long)src * ldzw]);
 }
 
 // ---------------------------------------------------------------------------

@@ -6,9 +6,11 @@
 #include "gemm_generic.cuh"
 #include "hemm_tma.cuh"
 #include "jacobi.cuh"
+#include "osj.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <numeric>
 #include <vector>
 
@@ -244,8 +246,8 @@ int trsm_impl(int64_t rows, int64_t n, const void* Rv, int64_t ldr, void* Vv, in
 }
 
 template <class T>
-int heev_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, double* w_host, void* ws,
-              size_t ws_bytes, int* sweeps_out, void* stream)
+int heev_jacobi_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, double* w_host, void* ws,
+                     size_t ws_bytes, int* sweeps_out, void* stream)
 {
     using C_ = typename Traits<T>::comp;
     const int n = (int)n64;
@@ -308,12 +310,143 @@ int heev_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, d
     for (int i = 0; i < n; ++i)
         w_host[i] = w[perm[i]];
     CB2_CUDA_OK(cudaMemcpyAsync(perm_dev, perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
-    jacobi_gather_kernel<T><<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, kcount(st)>>>(n, Zw, perm_dev, (T*)Zv, ldz);
+    jacobi_gather_kernel<T><<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, kcount(st)>>>(n, Zw, n, perm_dev, (T*)Zv, ldz);
     CB2_CUDA_OK(cudaGetLastError());
     CB2_CUDA_OK(cudaStreamSynchronize(st)); // perm (host vector) must outlive the copy
     if (sweeps_out)
         *sweeps_out = sweep + (converged ? 1 : 0);
     return converged ? 0 : 1;
+}
+
+// blocked one-sided Jacobi (osj.cuh).  workspace: B | Gs | Tm | glo | ghi | w | sigma | maxoff | nrot | perm
+template <class T>
+int heev_osj_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, double* w_host, void* ws,
+                  size_t ws_bytes, int* sweeps_out, void* stream)
+{
+    using C_ = typename Traits<T>::comp;
+    const int n = (int)n64;
+    cudaStream_t st = S(stream);
+    if (ws_bytes < chase_b200_heev_ws_bytes(n, Traits<T>::cplx))
+        return -3;
+    if (((uintptr_t)ws) & 15)
+        return -3;
+    const int ldb = (n + 1) & ~1; // 16-byte aligned columns for the TMA bulk copies
+    unsigned char* base = (unsigned char*)ws;
+    const size_t nb = (size_t)ldb * n;
+    C_* Bm = (C_*)base;
+    C_* Tm = Bm + nb;
+    C_* Gs = Tm + nb;
+    size_t off = (2 * nb + (size_t)n * n) * sizeof(C_);
+    double* glo = (double*)(base + off);
+    off += (size_t)n * sizeof(double);
+    double* ghi = (double*)(base + off);
+    off += (size_t)n * sizeof(double);
+    double* w_dev = (double*)(base + off);
+    off += (size_t)n * sizeof(double);
+    double* sigma = (double*)(base + off);
+    off += 16;
+    unsigned long long* maxoff = (unsigned long long*)(base + off);
+    off += 16;
+    int* nrot = (int*)(base + off);
+    off += 16;
+    int* perm_dev = (int*)(base + off);
+
+    osj_prepare_kernel<T><<<n, 256, 0, kcount(st)>>>(n, (const T*)Gv, ldg, Gs, glo, ghi);
+    osj_shift_kernel<C_><<<n, 256, 0, kcount(st)>>>(n, ldb, Gs, Bm, glo, ghi, sigma);
+    int nblk = (n + OSJ_B - 1) / OSJ_B;
+    if (nblk & 1)
+        ++nblk;
+    if (nblk < 2)
+        nblk = 2;
+    // rows per chunk: all of them if 16 columns fit into 208 KB of shared memory
+    const int rmax = (int)(208 * 1024 / (OSJ_K * sizeof(C_))) / 32 * 32;
+    const int rpc = std::min((n + 31) / 32 * 32, rmax);
+    const size_t smem = (size_t)OSJ_K * rpc * sizeof(C_);
+    CB2_CUDA_OK(cudaFuncSetAttribute(osj_round_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double tol = std::sqrt((double)n) * 2.220446049250313e-16;
+    const int max_sweeps = 60;
+    int sweep = 0, converged = 0;
+    for (; sweep < max_sweeps; ++sweep)
+    {
+        CB2_CUDA_OK(cudaMemsetAsync(maxoff, 0, 32, st)); // maxoff and nrot
+        for (int r = 0; r < nblk - 1; ++r)
+            osj_round_kernel<C_><<<nblk / 2, OSJ_THREADS, smem, kcount(st)>>>(n, ldb, rpc, nblk, r, Bm, tol, nrot,
+                                                                                maxoff);
+        struct
+        {
+            unsigned long long bits;
+            unsigned long long pad;
+            int nr;
+        } h;
+        CB2_CUDA_OK(cudaMemcpyAsync(&h, maxoff, 20, cudaMemcpyDeviceToHost, st));
+        CB2_CUDA_OK(cudaStreamSynchronize(st));
+        double mo;
+        std::memcpy(&mo, &h.bits, sizeof mo);
+        if (h.nr == 0 || mo < 64.0 * tol)
+        {
+            converged = 1;
+            break;
+        }
+    }
+    osj_normalize_kernel<C_><<<n, 256, 0, kcount(st)>>>(n, ldb, Bm);
+    {
+        GemmArgs<C_> p{};
+        p.M = n;
+        p.N = n;
+        p.K = n;
+        p.A = Gs;
+        p.lda = n;
+        p.B = Bm;
+        p.ldb = ldb;
+        p.C = Tm;
+        p.ldc = ldb;
+        p.alpha = from_real<C_>(1.0);
+        p.beta = czero<C_>();
+        int rc = gemm_launch<C_>(false, false, p, nullptr, 0, st);
+        if (rc)
+            return rc;
+    }
+    osj_rayleigh_kernel<C_><<<n, 256, 0, kcount(st)>>>(n, ldb, Bm, Tm, w_dev);
+    std::vector<double> w(n);
+    CB2_CUDA_OK(cudaMemcpyAsync(w.data(), w_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CB2_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<int> perm(n);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return w[a] < w[b]; });
+    for (int i = 0; i < n; ++i)
+        w_host[i] = w[perm[i]];
+    CB2_CUDA_OK(cudaMemcpyAsync(perm_dev, perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    jacobi_gather_kernel<T><<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, kcount(st)>>>(
+        n, Bm, ldb, perm_dev, (T*)Zv, ldz);
+    CB2_CUDA_OK(cudaGetLastError());
+    CB2_CUDA_OK(cudaStreamSynchronize(st));
+    if (sweeps_out)
+        *sweeps_out = sweep + (converged ? 1 : 0);
+    return converged ? 0 : 1;
+}
+
+// 0 = automatic (one-sided blocked Jacobi for n >= 48), 1 = two-sided cyclic Jacobi, 2 = one-sided always
+inline int heev_method()
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* e = getenv("CHASE_B200_HEEV");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+template <class T>
+int heev_impl(int64_t n, const void* Gv, int64_t ldg, void* Zv, int64_t ldz, double* w_host, void* ws, size_t ws_bytes,
+              int* sweeps_out, void* stream)
+{
+    if (n <= 0)
+        return 0;
+    const int m = heev_method();
+    if (m == 2 || (m == 0 && n >= 48))
+        return heev_osj_impl<T>(n, Gv, ldg, Zv, ldz, w_host, ws, ws_bytes, sweeps_out, stream);
+    return heev_jacobi_impl<T>(n, Gv, ldg, Zv, ldz, w_host, ws, ws_bytes, sweeps_out, stream);
 }
 
 template <class T>
@@ -573,9 +706,9 @@ extern "C" size_t chase_b200_heev_ws_bytes(int64_t n, int is_complex)
 {
     const size_t ce = is_complex ? 16 : 8;
     const size_t np = (size_t)((n + 1) & ~(int64_t)1);
-    size_t b = 2 * (size_t)n * n * ce;
+    size_t b = 3 * (size_t)(n + 1) * n * ce; // one-sided path: B | T | Gs (the two-sided path uses the first two)
     b += (np / 2) * sizeof(JRot) + 16;
-    b += (size_t)n * sizeof(double) + 32;
+    b += 3 * (size_t)n * sizeof(double) + 64;
     b += (size_t)n * sizeof(int) + 64;
     return b;
 }

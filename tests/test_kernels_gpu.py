@@ -269,6 +269,30 @@ def test_heev_clustered_and_degenerate():
     assert np.linalg.norm(G @ Z - Z * w) < 1e-12 * np.linalg.norm(G)
 
 
+@pytest.mark.parametrize("t,n", [("d", 1400), ("z", 700), ("d", 1029)])
+def test_heev_large_projected_matrix(t, n):
+    """Rayleigh-Ritz sized problems (BASELINE C2: nev+nex = 1400): dense spectrum 0.01..7 and the nearly diagonal
+    matrix of late iterations; eigenvalues to 1e-12 relative to ||G||, orthogonality and residual at n eps level."""
+    k = K()
+    rng = np.random.default_rng(n)
+    lam = np.linspace(0.01, 7.0, n)
+    X = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if t == "z" else 0)
+    Q, _ = np.linalg.qr(X)
+    E = rng.standard_normal((n, n)) * 1e-5
+    for G in ((Q * lam) @ Q.conj().T, np.diag(lam) + E + E.T):
+        G = ((G + G.conj().T) / 2).astype(DT[t])
+        ldg = (n + 15) // 16 * 16
+        dG = k.colmajor(G, ldg)
+        dZ = torch.zeros_like(dG)
+        w, sweeps, rc = k.heev(n, dG, ldg, dZ, ldg)
+        assert rc == 0 and sweeps <= 25
+        wref = np.linalg.eigvalsh(G)
+        assert np.max(np.abs(w - wref)) < 1e-12 * 7.0
+        Z = k.to_numpy(dZ, n)
+        assert np.linalg.norm(Z.conj().T @ Z - np.eye(n)) < 1e-11
+        assert np.linalg.norm(G @ Z - Z * w) / np.linalg.norm(G) < 5e-12
+
+
 def test_tridiag_eig_batched():
     k = K()
     M, batch = 25, 4
