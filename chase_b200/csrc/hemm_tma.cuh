@@ -42,7 +42,9 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <map>
 #include <type_traits>
+#include <utility>
 
 namespace cb2
 {
@@ -116,6 +118,22 @@ struct HemmParams
     double shift;        // scalar shift (used when theta == nullptr)
     const double* theta; // per-column shift
     int tiles_m, tiles_n;
+    long long span;      // k-blocks per CTA (stream-K); a multiple of nkt means whole tiles only
+    double* scratch;     // gridDim.x slots of BM*BN accumulators for incomplete tiles
+    unsigned* flags;     // one per CTA: epoch of the launch whose head part is parked in the slot
+    unsigned epoch;
+};
+
+// Stream-K work distribution.  The iteration space (tiles x k-blocks) is cut into gridDim.x equal contiguous spans,
+// so every CTA executes the same number of k-blocks (no wave quantisation: at N=20000, k=1400 the 1727 tiles were
+// 11.67 waves on 148 CTAs).  A span covers at most one incomplete tile at each end (host guarantees span >= one tile):
+// the CTA walks its span from the TOP, so the head part of a shared tile (k-blocks [0, x)) is produced first and
+// parked in a per-CTA scratch slot; the CTA that owns the tail part [x, nkt) reaches it LAST, adds the parked
+// partial sums and runs the epilogue.  Summation order is fixed (head + tail), so results are bit-reproducible.
+struct HemmSpan
+{
+    long long tile;
+    int kt_begin, kt_end;
 };
 
 template <class T, bool TA>
@@ -128,7 +146,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     constexpr bool CPLX = TR::cplx;
     using CF = HemmCfg<CPLX>;
     constexpr int BM = CF::BM, BN = CF::BN, BK = CF::BK, WM = CF::WM, WN = CF::WN, EPB = CF::EPB, ELEM = CF::ELEM;
-    constexpr int MI = WM / 8, NJ = WN / 8, STAGES = CF::STAGES;
+    constexpr int MI = WM / 8, NJ = WN / 8, STAGES = CF::STAGES, KSTEPS = CF::KSTEPS;
     constexpr int IMUL = CPLX ? 2 : 1; // the tensor maps see complex<double> as two FLOAT64
 
     extern __shared__ unsigned char smem_raw[];
@@ -148,8 +166,21 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     }
     __syncthreads();
 
-    const long long ntiles = (long long)p.tiles_m * p.tiles_n;
     const int nkt = (int)((p.K + BK - 1) / BK);
+    const long long it_begin = (long long)blockIdx.x * p.span;
+    const long long it_total = (long long)p.tiles_m * p.tiles_n * nkt;
+    const long long it_end = (it_begin + p.span < it_total) ? it_begin + p.span : it_total;
+    // next part of the span, walking down from it_hi
+    auto next_part = [&](long long it_hi) -> HemmSpan
+    {
+        HemmSpan sp;
+        sp.tile = (it_hi - 1) / nkt;
+        const long long first = sp.tile * nkt;
+        const long long lo = it_begin > first ? it_begin : first;
+        sp.kt_begin = (int)(lo - first);
+        sp.kt_end = (int)(it_hi - first);
+        return sp;
+    };
 
     if (warp == CF::CONSUMER_WARPS)
     {
@@ -159,11 +190,12 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
             uint32_t it = 0;
-            for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
+            for (long long hi = it_end; hi > it_begin;)
             {
-                const int tn = (int)(t % p.tiles_n), tm = (int)(t / p.tiles_n);
+                const HemmSpan sp = next_part(hi);
+                const int tn = (int)(sp.tile % p.tiles_n), tm = (int)(sp.tile / p.tiles_n);
                 const int m0 = tm * BM, n0 = tn * BN;
-                for (int kt = 0; kt < nkt; ++kt, ++it)
+                for (int kt = sp.kt_begin; kt < sp.kt_end; ++kt, ++it)
                 {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
@@ -181,6 +213,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
                     }
                     tma_load_2d(sb, &mapB, full, kt * BK * IMUL, n0);
                 }
+                hi -= (sp.kt_end - sp.kt_begin);
             }
         }
         return;
@@ -193,10 +226,49 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     // per-lane k offsets inside an 8-group for the two k-sets
     const int kq0 = 2 * q + (q & 1), kq1 = 2 * q + ((q & 1) ^ 1);
 
-    uint32_t it = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
+    // Byte offsets of this lane's fragments inside a stage, hoisted out of the k loop.  The swizzle XOR makes them
+    // non-affine in (i, ks) only through (i & AH) and ks; everything else is a compile-time stride that ends up as
+    // an immediate of the LDS.
+    //   M-major A tile (op N): m = wm*WM + 8i + c ; box = m / EPB, row = k, 16-byte chunk = (m % EPB * ELEM / 16) ^ (k & 7)
+    //   K-major tiles (B, and A for op C): row = n (or m), chunk = (k * ELEM / 16) ^ (row & 7)
+    constexpr int AH = (!TA && !CPLX) ? 2 : 1;                    // distinct i-classes of the M-major real tile
+    constexpr int A_ISTRIDE = TA ? 8 * 128 : (CPLX ? BK * 128 : BK * 128); // per AH-group of i (see below)
+    int a_off[AH][KSTEPS], b_off[KSTEPS];
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
     {
-        const int tn = (int)(t % p.tiles_n), tm = (int)(t / p.tiles_n);
+        const int kin = 8 * (ks >> 1) + ((ks & 1) ? kq1 : kq0);
+        const int k7 = kin & 7;
+#pragma unroll
+        for (int h = 0; h < AH; ++h)
+        {
+            if constexpr (TA)
+            {
+                const int m = wm * WM + ncol;
+                const int byte_in = kin * ELEM;
+                a_off[h][ks] = m * 128 + ((((byte_in >> 4) ^ (m & 7)) << 4) | (byte_in & 15));
+            }
+            else
+            {
+                const int m = wm * WM + 8 * h + c;
+                const int mblk = m / EPB, min_ = m % EPB;
+                const int byte_in = min_ * ELEM;
+                a_off[h][ks] = (mblk * BK + kin) * 128 + ((((byte_in >> 4) ^ k7) << 4) | (byte_in & 15));
+            }
+        }
+        {
+            const int n = wn * WN + ncol;
+            const int byte_in = kin * ELEM;
+            b_off[ks] = CF::A_BYTES + n * 128 + ((((byte_in >> 4) ^ (n & 7)) << 4) | (byte_in & 15));
+        }
+    }
+
+    uint32_t it = 0;
+    for (long long hi = it_end; hi > it_begin;)
+    {
+        const HemmSpan sp = next_part(hi);
+        hi -= (sp.kt_end - sp.kt_begin);
+        const int tn = (int)(sp.tile % p.tiles_n), tm = (int)(sp.tile / p.tiles_n);
         const long long m0 = (long long)tm * BM, n0 = (long long)tn * BN;
 
         double accr[NJ][MI][2];
@@ -211,45 +283,26 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
                     acci[j][i][0] = acci[j][i][1] = 0.0;
             }
 
-        for (int kt = 0; kt < nkt; ++kt, ++it)
+        for (int kt = sp.kt_begin; kt < sp.kt_end; ++kt, ++it)
         {
             const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(bars + 8 * s, ph);
-            const unsigned char* sa = gen_base + s * CF::STAGE_BYTES;
-            const unsigned char* sb = sa + CF::A_BYTES;
+            const unsigned char* st = gen_base + s * CF::STAGE_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < CF::KSTEPS; ++ks)
+            for (int ks = 0; ks < KSTEPS; ++ks)
             {
-                const int kin = 8 * (ks >> 1) + ((ks & 1) ? kq1 : kq0); // k inside the stage
-                const int k7 = kin & 7;
                 C_ fa[MI], fb[NJ];
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
                 {
-                    if constexpr (TA)
-                    {
-                        const int m = wm * WM + 8 * i + ncol;
-                        const int byte_in = kin * ELEM;
-                        const int off = m * 128 + ((((byte_in >> 4) ^ (m & 7)) << 4) | (byte_in & 15));
-                        fa[i] = *reinterpret_cast<const C_*>(sa + off);
-                    }
-                    else
-                    {
-                        const int m = wm * WM + 8 * i + c;
-                        const int mblk = m / EPB, min_ = m % EPB;
-                        const int byte_in = min_ * ELEM;
-                        const int off = (mblk * BK + kin) * 128 + ((((byte_in >> 4) ^ k7) << 4) | (byte_in & 15));
-                        fa[i] = *reinterpret_cast<const C_*>(sa + off);
-                    }
+                    // real M-major: i = 2g + h -> box g (+BK*128 bytes each); complex M-major: box i; K-major: row 8i
+                    const int h = (AH == 2) ? (i & 1) : 0;
+                    const int g = (AH == 2) ? (i >> 1) : i;
+                    fa[i] = *reinterpret_cast<const C_*>(st + a_off[h][ks] + g * A_ISTRIDE);
                 }
 #pragma unroll
                 for (int j = 0; j < NJ; ++j)
-                {
-                    const int n = wn * WN + 8 * j + ncol;
-                    const int byte_in = kin * ELEM;
-                    const int off = n * 128 + ((((byte_in >> 4) ^ (n & 7)) << 4) | (byte_in & 15));
-                    fb[j] = *reinterpret_cast<const C_*>(sb + off);
-                }
+                    fb[j] = *reinterpret_cast<const C_*>(st + b_off[ks] + j * (8 * 128));
                 if constexpr (!CPLX)
                 {
 #pragma unroll
@@ -281,6 +334,58 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(bars + 8 * (STAGES + s));
+        }
+
+        // ---------------- stream-K hand-over of incomplete tiles (consumer threads only: barrier 1) -----------
+        constexpr int NACC = NJ * MI * 2 * (CPLX ? 2 : 1);
+        const int ctid = tid; // consumers are threads 0..255
+        if (sp.kt_end < nkt)
+        {
+            // head part: park the raw accumulators for the CTA that owns the tail (blockIdx.x + 1)
+            double* slot = p.scratch + (size_t)blockIdx.x * (NACC * CF::CONSUMER_WARPS * 32);
+            int r = 0;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                    {
+                        __stcg(slot + (size_t)(r++) * 256 + ctid, accr[j][i][h]);
+                        if constexpr (CPLX)
+                            __stcg(slot + (size_t)(r++) * 256 + ctid, acci[j][i][h]);
+                    }
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ctid == 0)
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + blockIdx.x), "r"(p.epoch) : "memory");
+            continue;
+        }
+        if (sp.kt_begin > 0)
+        {
+            // tail part: wait for the head parked by CTA blockIdx.x - 1 and add it
+            if (ctid == 0)
+            {
+                unsigned v;
+                do
+                {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flags + blockIdx.x - 1) : "memory");
+                } while (v != p.epoch);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const double* slot = p.scratch + (size_t)(blockIdx.x - 1) * (NACC * CF::CONSUMER_WARPS * 32);
+            int r = 0;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                    {
+                        accr[j][i][h] += __ldcg(slot + (size_t)(r++) * 256 + ctid);
+                        if constexpr (CPLX)
+                            acci[j][i][h] += __ldcg(slot + (size_t)(r++) * 256 + ctid);
+                    }
         }
 
         // ------------------------------ epilogue ------------------------------
@@ -417,6 +522,42 @@ inline bool hemm_tma_supported(int64_t M, int64_t K, int64_t k, const void* A, i
     return true;
 }
 
+// Scratch for the stream-K hand-over: one slot of BM*BN accumulators and one flag per CTA, allocated once per
+// (device, stream) so that launches on different streams never share slots.
+struct HemmScratch
+{
+    double* slots = nullptr;
+    unsigned* flags = nullptr;
+    unsigned epoch = 0;
+};
+inline HemmScratch* hemm_scratch(int dev, cudaStream_t st, int sms)
+{
+    static std::map<std::pair<int, cudaStream_t>, HemmScratch> pool;
+    auto key = std::make_pair(dev, st);
+    auto it = pool.find(key);
+    if (it != pool.end())
+        return &it->second;
+    HemmScratch sc;
+    const size_t slot_doubles = (size_t)HemmCfg<false>::BM * HemmCfg<false>::BN; // == complex BM*BN*2
+    if (cudaMalloc(&sc.slots, (size_t)sms * slot_doubles * sizeof(double)) != cudaSuccess)
+        return nullptr;
+    if (cudaMalloc(&sc.flags, (size_t)sms * sizeof(unsigned)) != cudaSuccess)
+        return nullptr;
+    if (cudaMemset(sc.flags, 0, (size_t)sms * sizeof(unsigned)) != cudaSuccess)
+        return nullptr;
+    return &(pool[key] = sc);
+}
+inline bool hemm_streamk_disabled()
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* e = getenv("CHASE_B200_NO_STREAMK");
+        v = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 template <class T>
 inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Traits<T>::comp alpha, const T* A,
                            int64_t lda, const T* B, int64_t ldb, typename Traits<T>::comp beta, T* C, int64_t ldc,
@@ -477,7 +618,27 @@ inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Tr
     CB2_CUDA_OK(cudaGetDevice(&dev));
     CB2_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long ntiles = (long long)p.tiles_m * p.tiles_n;
-    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    const long long nkt = (K + CF::BK - 1) / CF::BK;
+    int grid;
+    if (ntiles >= sms && !hemm_streamk_disabled())
+    {
+        // stream-K: equal spans of k-blocks, at most one incomplete tile at each end of a span
+        grid = sms;
+        p.span = (ntiles * nkt + grid - 1) / grid;
+    }
+    else
+    {
+        // whole tiles per CTA (round-robin over tiles would need more than one span per CTA: use contiguous tiles)
+        grid = (int)(ntiles < sms ? ntiles : sms);
+        const long long tiles_per_cta = (ntiles + grid - 1) / grid;
+        p.span = tiles_per_cta * nkt;
+    }
+    HemmScratch* sc = hemm_scratch(dev, st, sms);
+    if (!sc)
+        return -1;
+    p.scratch = sc->slots;
+    p.flags = sc->flags;
+    p.epoch = ++sc->epoch;
     if (ta)
     {
         CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -173,6 +173,7 @@ public:
     void HEMM(std::size_t block, T alpha, T beta, std::size_t offset_left, std::size_t offset_right = 0) override
     {
         flush_perm();
+        resid_ready_ = false;
         const std::size_t ncols = (offset_right < block) ? block - offset_right : 0;
         if (ncols > 0)
         {
@@ -198,6 +199,7 @@ public:
     void QR(std::size_t /*fixednev*/, R cond) override
     {
         flush_perm();
+        resid_ready_ = false;
         // keep the locked vectors: CholQR runs on all nev+nex columns
         CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)locked_, dV1_, (int64_t)ld_, dV2_, (int64_t)ld_, stream_));
 
@@ -253,6 +255,7 @@ public:
     void RR(R* ritzv, std::size_t block) override
     {
         flush_perm();
+        resid_ready_ = false;
         if (block == 0)
             return;
         T* Q = dV1_ + locked_ * ld_;
@@ -272,10 +275,23 @@ public:
         heev_sweeps_ += sweeps;
         for (std::size_t i = 0; i < block; ++i)
             ritzv[i] = (R)w[i];
+        // residual block while A Q is at hand: R = (A Q) Z - (Q Z) Theta  (the reference runs a second A V,
+        // cuda/residuals.hpp:92-110; N k^2 instead of N^2 k flops here)
+        T* Rm = dW_ + locked_ * ld_;
+        CB2_KCHECK(KK::gemm(0, 0, (int64_t)N_, (int64_t)block, (int64_t)block, 1.0, 0.0, W, (int64_t)ld_, dZ_,
+                            (int64_t)ldg_, 0.0, 0.0, Rm, (int64_t)ld_, 0, nullptr, 0, stream_));
         // V2 = Q Z ; swap
         CB2_KCHECK(KK::gemm(0, 0, (int64_t)N_, (int64_t)block, (int64_t)block, 1.0, 0.0, Q, (int64_t)ld_, dZ_,
                             (int64_t)ldg_, 0.0, 0.0, W, (int64_t)ld_, 0, nullptr, 0, stream_));
         std::swap(dV1_, dV2_);
+        for (std::size_t i = 0; i < block; ++i)
+            w[i] = (double)ritzv[i]; // rounded to Base<T> like the values the driver passes to Resd
+        CB2_CHECK(cudaMemcpyAsync(dTheta_, w.data(), block * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        CB2_KCHECK(KK::axpy_cols((int64_t)N_, (int64_t)block, dTheta_, -1.0, 0.0, dV1_ + locked_ * ld_, (int64_t)ld_,
+                                 Rm, (int64_t)ld_, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_)); // w is a host temporary
+        resid_ready_ = true;
+        resid_block_ = block;
     }
 
     void Sort(R*, R*, R*) override {}
@@ -287,14 +303,22 @@ public:
         if (k == 0)
             return;
         std::vector<double> th(k);
-        for (std::size_t i = 0; i < k; ++i)
-            th[i] = (double)ritzv[i];
-        CB2_CHECK(cudaMemcpyAsync(dTheta_, th.data(), k * sizeof(double), cudaMemcpyHostToDevice, stream_));
-        T* V = dV1_ + locked_ * ld_;
         T* W = dV2_ + locked_ * ld_;
-        // W = A V - V diag(theta)
-        CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)k, 1.0, 0.0, dH_, (int64_t)ld_, V, (int64_t)ld_, 0.0, 0.0, W,
-                            (int64_t)ld_, 0.0, dTheta_, stream_));
+        if (resid_ready_ && resid_block_ == k && !std::getenv("CHASE_B200_RESID_HEMM"))
+        {
+            W = dW_ + locked_ * ld_; // prepared by RR
+        }
+        else
+        {
+            for (std::size_t i = 0; i < k; ++i)
+                th[i] = (double)ritzv[i];
+            CB2_CHECK(cudaMemcpyAsync(dTheta_, th.data(), k * sizeof(double), cudaMemcpyHostToDevice, stream_));
+            T* V = dV1_ + locked_ * ld_;
+            // W = A V - V diag(theta), shift folded into the HEMM epilogue
+            CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)k, 1.0, 0.0, dH_, (int64_t)ld_, V, (int64_t)ld_, 0.0, 0.0, W,
+                                (int64_t)ld_, 0.0, dTheta_, stream_));
+        }
+        resid_ready_ = false;
         CB2_KCHECK(KK::colnorms((int64_t)N_, (int64_t)k, W, (int64_t)ld_, dNorms_, 1, stream_));
         std::vector<double> nr(k);
         CB2_CHECK(cudaMemcpyAsync(nr.data(), dNorms_, k * sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -462,6 +486,7 @@ private:
                                        (int64_t)ld_, stream_));
             CB2_CHECK(cudaStreamSynchronize(stream_)); // idx is a host temporary
             gathers_++;
+            resid_ready_ = false; // dW_ was the gather scratch
         }
         reset_perm();
     }
@@ -595,6 +620,8 @@ private:
     std::vector<R> resid_;
     std::vector<int> perm_;
     bool perm_dirty_ = false;
+    bool resid_ready_ = false; // dW_ holds (A Q) Z - (Q Z) Theta of the last RR
+    std::size_t resid_block_ = 0;
     std::size_t locked_ = 0;
     double shift_ = 0.0;
     std::size_t lanczosIter_ = 0, numLanczos_ = 0;

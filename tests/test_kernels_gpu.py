@@ -155,6 +155,51 @@ def test_hemm_rect_local_block(t, ta, M, Kd, kcols):
     assert relerr(k.to_numpy(dC, M), ref) < TOL[t]
 
 
+@pytest.mark.parametrize("t", ["d", "z"])
+@pytest.mark.parametrize("ta", [0, 1])
+def test_hemm_streamk_many_tiles(t, ta):
+    """>= 148 output tiles: the stream-K schedule splits tiles across CTAs (head part parked in scratch, tail part
+    adds it).  Checked against a float64 matmul, twice (the second launch reuses the scratch slots), plus bitwise
+    reproducibility of the two launches."""
+    k = K()
+    M, Kd, kcols = (4100, 3000, 650) if t == "d" else (3000, 2100, 330)
+    rng = np.random.default_rng(5 + ta)
+    A = rnd(rng, (Kd, M) if ta else (M, Kd), t)
+    B = rnd(rng, (Kd, kcols), t)
+    C = rnd(rng, (M, kcols), t)
+    alpha, beta = 0.37, -1.25
+    opA = A.conj().T if ta else A
+    ref = alpha * (opA @ B) + beta * C
+    lda = (A.shape[0] + 15) // 16 * 16
+    ldb = (Kd + 15) // 16 * 16
+    ldc = (M + 15) // 16 * 16
+    dA, dB = k.colmajor(A, lda), k.colmajor(B, ldb)
+    outs = []
+    for _ in range(2):
+        dC = k.colmajor(C, ldc)
+        k.hemm_rect(ta, M, Kd, kcols, alpha, dA, lda, dB, ldb, beta, dC, ldc)
+        torch.cuda.synchronize()
+        outs.append(k.to_numpy(dC, M))
+        assert relerr(outs[-1], ref) < TOL[t]
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_hemm_streamk_square_with_shift():
+    k = K()
+    n, kcols = 4500, 700
+    rng = np.random.default_rng(3)
+    A = rnd(rng, (n, n), "d")
+    A = (A + A.T) / 2
+    B = rnd(rng, (n, kcols), "d")
+    C = rnd(rng, (n, kcols), "d")
+    ref = co.gemm_filter_step(A, B, C, 0.02, -0.4, 1.5)
+    ld = (n + 15) // 16 * 16
+    dA, dB, dC = k.colmajor(A, ld), k.colmajor(B, ld), k.colmajor(C, ld)
+    k.hemm(n, kcols, 0.02, dA, ld, dB, ld, -0.4, dC, ld, 1.5)
+    torch.cuda.synchronize()
+    assert relerr(k.to_numpy(dC, n), ref) < 1e-12
+
+
 def _fixture(name):
     p = os.path.join(os.path.dirname(__file__), "golden", "qr_fixtures", name)
     return p if os.path.exists(p) else None
