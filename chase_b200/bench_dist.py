@@ -48,20 +48,28 @@ def lowrank_terms(N: int, cplx: bool):
     return lam, np.stack(X, 1), np.stack(Y, 1), np.array(coef)
 
 
-def local_block(N, gr, gc, cplx, device):
+def local_block(N, gr, gc, cplx, device, transposed=False):
+    """This rank's block A[gr, gc] as a torch tensor (m_loc, n_loc); transposed=True returns it as (n_loc, m_loc)
+    row-major, i.e. the column-major m_loc x n_loc array the solver wants, without an extra copy."""
     import torch
 
     lam, X, Y, coef = lowrank_terms(N, cplx)
     dt = torch.complex128 if cplx else torch.float64
     Xl = torch.from_numpy(X[gr, :] * coef[None, :]).to(device).to(dt)
     Yl = torch.from_numpy(Y[gc, :]).to(device).to(dt)
-    A = Xl @ Yl.conj().T  # m_loc x n_loc
     # global diagonal entries inside this block
     pos = {int(g): k for k, g in enumerate(gc)}
     rows = [k for k, g in enumerate(gr) if int(g) in pos]
     cols = [pos[int(gr[k])] for k in rows]
-    if rows:
-        A[rows, cols] += torch.from_numpy(lam[gr[rows]]).to(device).to(dt)
+    dvals = torch.from_numpy(lam[gr[rows]]).to(device).to(dt) if rows else None
+    if transposed:
+        A = Yl.conj() @ Xl.T  # n_loc x m_loc
+        if rows:
+            A[cols, rows] += dvals
+    else:
+        A = Xl @ Yl.conj().T  # m_loc x n_loc
+        if rows:
+            A[rows, cols] += dvals
     return A, lam
 
 

@@ -120,16 +120,22 @@ class PChASE:
         self.i, self.j = grid_coords(r, c, major, world.rank)
         self.m = local_size(N, r, mb, self.i)
         self.n = local_size(N, c, nb, self.j)
-        H_loc = np.asarray(H_loc)
-        if H_loc.shape != (self.m, self.n):
-            raise ValueError(f"local block must be {self.m} x {self.n}, got {H_loc.shape}")
-        if not H_loc.flags.f_contiguous:
-            H_loc = np.asfortranarray(H_loc)
-        self.pfx = _PFX[H_loc.dtype]
+        if isinstance(H_loc, np.dtype) or isinstance(H_loc, type):
+            # no host matrix: the block will be handed over on the device (load_device_matrix)
+            self._dtype = np.dtype(H_loc)
+            H_loc = None
+        else:
+            H_loc = np.asarray(H_loc)
+            if H_loc.shape != (self.m, self.n):
+                raise ValueError(f"local block must be {self.m} x {self.n}, got {H_loc.shape}")
+            if not H_loc.flags.f_contiguous:
+                H_loc = np.asfortranarray(H_loc)
+            self._dtype = H_loc.dtype
+        self.pfx = _PFX[self._dtype]
         self.rdt = _REAL[self.pfx]
         self.H = H_loc
         if V_loc is None:
-            V_loc = np.zeros((max(self.m, 1), self.nevex), dtype=H_loc.dtype, order="F")
+            V_loc = np.zeros((max(self.m, 1), self.nevex), dtype=self._dtype, order="F")
         assert V_loc.flags.f_contiguous and V_loc.shape == (max(self.m, 1), self.nevex)
         self.V = V_loc
         self.ritzv = np.zeros(self.nevex, dtype=self.rdt)
@@ -140,15 +146,25 @@ class PChASE:
         comm = ctypes.byref(world.handle)
         if mb == 0 and nb == 0:
             getattr(self._lib, f"p{self.pfx}chase_init_")(
-                _i(N), _i(nev), _i(nex), _i(self.m), _i(self.n), _p(self.H), ldh, _p(self.V), _p(self.ritzv),
+                _i(N), _i(nev), _i(nex), _i(self.m), _i(self.n), self._hp(), ldh, _p(self.V), _p(self.ritzv),
                 _i(r), _i(c), gm, comm, ctypes.byref(flag))
         else:
             getattr(self._lib, f"p{self.pfx}chase_init_blockcyclic_")(
-                _i(N), _i(nev), _i(nex), _i(mb), _i(nb), _p(self.H), ldh, _p(self.V), _p(self.ritzv), _i(r), _i(c),
+                _i(N), _i(nev), _i(nex), _i(mb), _i(nb), self._hp(), ldh, _p(self.V), _p(self.ritzv), _i(r), _i(c),
                 gm, _i(0), _i(0), comm, ctypes.byref(flag))
         if flag.value != 1:
             raise RuntimeError("chase_b200: p?chase_init_ failed")
         self._alive = True
+
+    def _hp(self):
+        return _p(self.H) if self.H is not None else ctypes.c_void_p(0)
+
+    def load_device_matrix(self, dev_ptr: int, ld: int):
+        """Hand over this rank's block as a column-major device array (e.g. a torch tensor's data_ptr())."""
+        rc = self._lib.chase_b200_dist_load_device_matrix_(ctypes.c_char_p(self.pfx.encode()), ctypes.c_void_p(dev_ptr),
+                                                           ctypes.byref(ctypes.c_longlong(ld)))
+        if rc != 0:
+            raise RuntimeError("chase_b200: device matrix hand-over failed")
 
     def row_indices(self):
         return global_indices(self.N, self.grid[0], self.mb, self.i)

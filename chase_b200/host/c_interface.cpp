@@ -17,6 +17,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 extern "C" int chase_b200_device_sync(void) { return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1; }
@@ -544,6 +545,42 @@ extern "C"
     CB2_DIST_API(z, cd, CHASE_B200_CD, double, PZ)
     CB2_DIST_API(c, cf, CHASE_B200_CF, float, PC)
 #undef CB2_DIST_API
+
+    // Device-resident input for matrices that should never exist on the host (C4: 28.8 GB per GPU): copies a
+    // column-major device block (m_loc x n_loc, leading dimension ld_src) into the active distributed solver and marks
+    // it resident, so that p?chase_ does not read the host pointer given at init.
+    int chase_b200_dist_load_device_matrix_(char* type, const void* src_dev, long long* ld_src)
+    {
+        auto load = [&](auto& inst) -> int
+        {
+            using S = std::remove_reference_t<decltype(*inst.solver)>;
+            if (!inst.solver)
+                return -1;
+            auto* sv = inst.solver.get();
+            using TT = std::remove_pointer_t<decltype(sv->device_H())>;
+            if (sv->local_rows() > 0 && sv->local_cols() > 0)
+            {
+                if (cudaMemcpy2DAsync(sv->device_H(), sv->device_lda() * sizeof(TT), src_dev,
+                                      (size_t)*ld_src * sizeof(TT), sv->local_rows() * sizeof(TT), sv->local_cols(),
+                                      cudaMemcpyDeviceToDevice, sv->stream()) != cudaSuccess)
+                    return -1;
+                if (cudaStreamSynchronize(sv->stream()) != cudaSuccess)
+                    return -1;
+            }
+            sv->mark_matrix_on_device();
+            g_matrix_resident = 1;
+            (void)sizeof(S);
+            return 0;
+        };
+        switch (*type)
+        {
+            case 'd': return load(PD::get());
+            case 's': return load(PS::get());
+            case 'z': return load(PZ::get());
+            case 'c': return load(PC::get());
+        }
+        return -1;
+    }
 
     // ---- communicator bootstrap (include/chase_b200_comm.h) ------------------------------------------------
     int chase_b200_comm_unique_id(void* id_out)

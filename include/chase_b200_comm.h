@@ -44,6 +44,11 @@ extern "C"
        redistributeImpl (linalg/distMatrix/distMultiVector.hpp:2817-2909). */
     int chase_b200_redistribution_map(long long N, int src_nprocs, long long src_nb, long long src_stride,
                                       int dst_nprocs, long long dst_nb, int pd, long long* out);
+    /* Device-resident input: copies this rank's column-major device block (leading dimension *ld_src) into the active
+       distributed solver of scalar type *type ('s','d','c','z') and marks it resident; subsequent p?chase_ calls do not
+       read the host matrix pointer (which may then be NULL at init).  For matrices that must never exist on the host
+       (BASELINE config C4: 28.8 GB per GPU). */
+    int chase_b200_dist_load_device_matrix_(char* type, const void* src_dev, long long* ld_src);
     /* grid coordinates of `rank` in a dim0 x dim1 grid with 'R'ow- or 'C'olumn-major rank order */
     int chase_b200_grid_coords(int dim0, int dim1, char grid_major, int rank, int* row_out, int* col_out);
 
