@@ -78,11 +78,46 @@ def run_case(world, name, grid, layout, major):
                 filtered_vecs=res.filtered_vecs, max_rel_eig=rel, max_resid=float(rr.max()), orth=orth, fails=fails)
 
 
+def run_sequence(world, name, grid, layout, major):
+    """tests/noinput.cpp-style sequence on a grid: problem 0 random start, then perturbed matrices re-using the
+    distributed V / ritzv (mode 'A'); the local host blocks are re-read at every solve."""
+    g = load(name)
+    dt = DT[g["type"]]
+    N, nev, nex = g["N"], g["nev"], g["nex"]
+    H = co.clement(N, dt)
+    nb = 0 if layout == "block" else 32
+    r, c = grid
+    i, j = cd.grid_coords(r, c, major, world.rank)
+    gr, gc = cd.global_indices(N, r, nb, i), cd.global_indices(N, c, nb, j)
+    nseq = len(g["problems"])
+    stream = co.mt_normal(1337, (2 if g["type"] == "z" else 1) * nseq * N * N)
+    pos, fails, its = 0, [], []
+    with cd.PChASE(world, N, nev, nex, np.asfortranarray(H[np.ix_(gr, gc)]), grid=grid, major=major, mb=nb, nb=nb) as s:
+        for idx, p in enumerate(g["problems"]):
+            res = s.solve(deg=g["deg"], tol=g["tol"], mode="R" if idx == 0 else "A", trace=True)
+            its.append(res.iterations)
+            ref, got = parse_trace(p["trace"]), parse_trace(res.trace)
+            if res.iterations != p["iterations"] or res.filtered_vecs != p["filtered_vecs"]:
+                fails.append(f"problem {idx}: iterations/filtered {res.iterations}/{res.filtered_vecs} != "
+                             f"{p['iterations']}/{p['filtered_vecs']}")
+            if [(b, o) for (b, o, _, _) in got["hemm"]] != [(b, o) for (b, o, _, _) in ref["hemm"]]:
+                fails.append(f"problem {idx}: HEMM schedule differs")
+            refv = np.array(p["ritzv"][:nev])
+            rel = float(np.max(np.abs(res.ritzv[:nev] - refv) / np.abs(refv)))
+            if rel > 1e-10:
+                fails.append(f"problem {idx}: eigenvalues off by {rel:.2e}")
+            if idx + 1 < nseq:
+                pos += co.perturb_hermitian(H, stream[pos:], 1e-4)
+                s.H[...] = H[np.ix_(gr, gc)]
+    return dict(case=name + " (sequence)", grid=f"{r}x{c}", layout=layout, major=major, iterations=its, fails=fails)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="serial_clement_d_N256,serial_clement_z_N256,c1_clement_d_N1001,c2s_uniform_d_N2000")
     ap.add_argument("--grid", default="")
     ap.add_argument("--out", default="")
+    ap.add_argument("--no-seq", action="store_true")
     a = ap.parse_args()
     world = cd.World()
     grids = [tuple(int(x) for x in a.grid.split("x"))] if a.grid else [cd.grid_dims(world.size)]
@@ -97,6 +132,15 @@ def main():
                 bad += len(r["fails"])
                 if world.rank == 0:
                     print(("FAIL " if r["fails"] else "ok   ") + json.dumps(r), flush=True)
+    if not a.no_seq:
+        for grid in grids[:1]:
+            for layout, major in (("block", "R"), ("cyclic", "R")):
+                for name in ("seq_clement_d_N400", "seq_clement_z_N400"):
+                    r = run_sequence(world, name, grid, layout, major)
+                    results.append(r)
+                    bad += len(r["fails"])
+                    if world.rank == 0:
+                        print(("FAIL " if r["fails"] else "ok   ") + json.dumps(r), flush=True)
     if world.rank == 0 and a.out:
         json.dump(results, open(a.out, "w"), indent=1)
     world.close()

@@ -13,7 +13,7 @@ INC = os.path.join(ROOT, "include")
 
 def _declared(header):
     src = subprocess.check_output(["gcc", "-E", "-P", os.path.join(INC, header)], text=True)
-    names = set(re.findall(r"\b((?:chase_b200_\w+)|(?:[sdcz]chase_\w*_)|(?:chase_\w+_))\s*\(", src))
+    names = set(re.findall(r"\b((?:chase_b200_\w+)|(?:p?[sdcz]chase_\w*_)|(?:chase_\w+_))\s*\(", src))
     return sorted(names)
 
 
@@ -26,10 +26,10 @@ def native():
     return ctypes.CDLL(LIB_PATH)
 
 
-@pytest.mark.parametrize("header", ["chase_b200_kernels.h", "chase_c_interface.h"])
+@pytest.mark.parametrize("header", ["chase_b200_kernels.h", "chase_c_interface.h", "chase_b200_comm.h"])
 def test_every_declared_symbol_is_exported(native, header):
     names = _declared(header)
-    assert len(names) > 20
+    assert len(names) > (20 if header != "chase_b200_comm.h" else 8)
     missing = [n for n in names if not hasattr(native, n)]
     assert not missing, f"declared in {header} but not exported: {missing}"
 
