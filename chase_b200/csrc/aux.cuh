@@ -121,53 +121,84 @@ __global__ void __launch_bounds__(1024) normalize_cols_kernel(long long rows, T*
         x[i] = narrow<T>(cmul(inv, (C)widen(x[i])));
 }
 
-// Y[j, v] = sum_i conj(A[i, j]) * X[i, v]   (one warp per column j of A)
+// Y[j, v] = sum_i conj(A[i, j]) * X[i, v].  One warp per group of GEMV_CJ columns of A: every X value loaded is used
+// for GEMV_CJ columns, so the L2 traffic for X (which every warp has to stream in full) is 1/GEMV_CJ of A's instead
+// of NV times A's; A itself is read exactly once from HBM with GEMV_CJ * 2 independent 256-byte requests in flight
+// per warp.
+constexpr int GEMV_CJ = 4;
 template <class T, int NV>
 __global__ void __launch_bounds__(256) gemv_conjT_kernel(long long rows, long long cols, const T* A, long long lda,
                                                           const T* X, long long ldx, T* Y, long long ldy)
 {
     using C = typename Traits<T>::comp;
+    constexpr int CJ = GEMV_CJ;
     const int lane = threadIdx.x & 31;
     const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long j = warp; j < cols; j += nwarps)
+    const long long ngroups = (cols + CJ - 1) / CJ;
+    for (long long g = warp; g < ngroups; g += nwarps)
     {
-        const T* a = A + j * lda;
-        C acc[NV];
+        const long long j0 = g * CJ;
+        const T* a[CJ];
 #pragma unroll
-        for (int v = 0; v < NV; ++v)
-            acc[v] = czero<C>();
+        for (int c = 0; c < CJ; ++c)
+            a[c] = A + (j0 + c < cols ? j0 + c : cols - 1) * lda; // clamped: duplicates are not stored
+        C acc[CJ][NV];
+#pragma unroll
+        for (int c = 0; c < CJ; ++c)
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                acc[c][v] = czero<C>();
         long long i = lane;
-        for (; i + 96 < rows; i += 128)
+        for (; i + 32 < rows; i += 64)
         {
-            C av[4];
+            C av[2][CJ], xv[2][NV];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                av[u] = cconj(widen(a[i + 32 * u]));
+            for (int u = 0; u < 2; ++u)
+            {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+                for (int c = 0; c < CJ; ++c)
+                    av[u][c] = cconj(widen(a[c][i + 32 * u]));
 #pragma unroll
                 for (int v = 0; v < NV; ++v)
-                    acc[v] = cadd(acc[v], cmul(av[u], (C)widen(X[i + 32 * u + v * ldx])));
+                    xv[u][v] = widen(X[i + 32 * u + v * ldx]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int c = 0; c < CJ; ++c)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        acc[c][v] = cadd(acc[c][v], cmul(av[u][c], xv[u][v]));
         }
         for (; i < rows; i += 32)
         {
-            const C av = cconj(widen(a[i]));
+            C xv[NV];
 #pragma unroll
             for (int v = 0; v < NV; ++v)
-                acc[v] = cadd(acc[v], cmul(av, (C)widen(X[i + v * ldx])));
+                xv[v] = widen(X[i + v * ldx]);
+#pragma unroll
+            for (int c = 0; c < CJ; ++c)
+            {
+                const C av = cconj(widen(a[c][i]));
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    acc[c][v] = cadd(acc[c][v], cmul(av, xv[v]));
+            }
         }
 #pragma unroll
-        for (int v = 0; v < NV; ++v)
-        {
-            C r;
-            if constexpr (Traits<T>::cplx)
-                r = cxd{warp_sum(acc[v].re), warp_sum(acc[v].im)};
-            else
-                r = warp_sum(acc[v]);
-            if (lane == 0)
-                Y[j + v * ldy] = narrow<T>(r);
-        }
+        for (int c = 0; c < CJ; ++c)
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+            {
+                C r;
+                if constexpr (Traits<T>::cplx)
+                    r = cxd{warp_sum(acc[c][v].re), warp_sum(acc[c][v].im)};
+                else
+                    r = warp_sum(acc[c][v]);
+                if (lane == 0 && j0 + c < cols)
+                    Y[j0 + c + v * ldy] = narrow<T>(r);
+            }
     }
 }
 

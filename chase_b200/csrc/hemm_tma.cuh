@@ -66,7 +66,10 @@ struct HemmCfg
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = CPLX ? 8 : 6;
     static constexpr int CONSUMER_WARPS = 8;
-    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+    // 8 consumer warps (2 warpgroups) + 1 producer warpgroup of which one lane works.  Register budget is per SM
+    // sub-partition: setmaxnreg moves registers from the producer warpgroup (40) to the consumers (232), so the 64
+    // FP64 accumulators + fragments + hoisted offsets of a consumer thread never spill.
+    static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 2 * STAGES * 8;
 };
 
@@ -182,10 +185,11 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
         return sp;
     };
 
-    if (warp == CF::CONSUMER_WARPS)
+    if (warp >= CF::CONSUMER_WARPS)
     {
         // ------------------------------ producer ------------------------------
-        if (lane == 0)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == CF::CONSUMER_WARPS && lane == 0)
         {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     }
 
     // -------------------------------- consumers --------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int wm = warp % CF::WARPS_M, wn = warp / CF::WARPS_M;
     const int q = lane & 3, c = lane >> 2;
     const int ncol = (c & 1) | ((c & 2) << 1) | ((c & 4) >> 1); // {0,1,4,5,2,3,6,7}
@@ -283,11 +288,15 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
                     acci[j][i][0] = acci[j][i][1] = 0.0;
             }
 
-        for (int kt = sp.kt_begin; kt < sp.kt_end; ++kt, ++it)
+        // Ragged last N tile: 8-column groups beyond k are skipped (warp-uniform), so a tile with <= BN/2 valid columns
+        // keeps only one warp per SM sub-partition busy and costs about half a tile.
+        const int nvalid = (int)((p.k - n0) < (long long)BN ? (p.k - n0) : (long long)BN);
+        int jmax = (nvalid - wn * WN + 7) / 8;
+        jmax = jmax < 0 ? 0 : (jmax > NJ ? NJ : jmax);
+
+        auto k_block = [&](const unsigned char* st, auto full_tag)
         {
-            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-            mbar_wait(bars + 8 * s, ph);
-            const unsigned char* st = gen_base + s * CF::STAGE_BYTES;
+            constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks)
             {
@@ -302,35 +311,51 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
                 }
 #pragma unroll
                 for (int j = 0; j < NJ; ++j)
-                    fb[j] = *reinterpret_cast<const C_*>(st + b_off[ks] + j * (8 * 128));
+                    if (FULL || j < jmax)
+                        fb[j] = *reinterpret_cast<const C_*>(st + b_off[ks] + j * (8 * 128));
                 if constexpr (!CPLX)
                 {
 #pragma unroll
                     for (int j = 0; j < NJ; ++j)
+                        if (FULL || j < jmax)
+                        {
 #pragma unroll
-                        for (int i = 0; i < MI; ++i)
-                            dmma884(accr[j][i][0], accr[j][i][1], fb[j], fa[i]);
+                            for (int i = 0; i < MI; ++i)
+                                dmma884(accr[j][i][0], accr[j][i][1], fb[j], fa[i]);
+                        }
                 }
                 else
                 {
 #pragma unroll
                     for (int j = 0; j < NJ; ++j)
-                    {
-                        // TA: the A operand enters conjugated: (ar - i ai)(br + i bi)
-                        const double bre = fb[j].re, bim = fb[j].im;
-                        const double s_ri = TA ? fb[j].im : -fb[j].im; // multiplies a.im into the real part
-                        const double s_ir = TA ? -fb[j].re : fb[j].re; // multiplies a.im into the imaginary part
-#pragma unroll
-                        for (int i = 0; i < MI; ++i)
+                        if (FULL || j < jmax)
                         {
-                            dmma884(accr[j][i][0], accr[j][i][1], bre, fa[i].re);
-                            dmma884(accr[j][i][0], accr[j][i][1], s_ri, fa[i].im);
-                            dmma884(acci[j][i][0], acci[j][i][1], s_ir, fa[i].im);
-                            dmma884(acci[j][i][0], acci[j][i][1], bim, fa[i].re);
+                            // TA: the A operand enters conjugated: (ar - i ai)(br + i bi)
+                            const double bre = fb[j].re, bim = fb[j].im;
+                            const double s_ri = TA ? fb[j].im : -fb[j].im; // multiplies a.im into the real part
+                            const double s_ir = TA ? -fb[j].re : fb[j].re; // multiplies a.im into the imaginary part
+#pragma unroll
+                            for (int i = 0; i < MI; ++i)
+                            {
+                                dmma884(accr[j][i][0], accr[j][i][1], bre, fa[i].re);
+                                dmma884(accr[j][i][0], accr[j][i][1], s_ri, fa[i].im);
+                                dmma884(acci[j][i][0], acci[j][i][1], s_ir, fa[i].im);
+                                dmma884(acci[j][i][0], acci[j][i][1], bim, fa[i].re);
+                            }
                         }
-                    }
                 }
             }
+        };
+
+        for (int kt = sp.kt_begin; kt < sp.kt_end; ++kt, ++it)
+        {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(bars + 8 * s, ph);
+            const unsigned char* st = gen_base + s * CF::STAGE_BYTES;
+            if (jmax == NJ)
+                k_block(st, std::true_type{});
+            else if (jmax > 0)
+                k_block(st, std::false_type{});
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(bars + 8 * (STAGES + s));
@@ -506,14 +531,14 @@ inline bool hemm_tma_disabled()
 // FP64 storage only (TMA moves raw bytes; FP32 storage is widened by the generic kernel).
 template <class T>
 inline bool hemm_tma_supported(int64_t M, int64_t K, int64_t k, const void* A, int64_t lda, const void* B,
-                               int64_t ldb, const void* C, int64_t ldc)
+                               int64_t ldb, const void* C, int64_t ldc, int64_t min_m = 256, int64_t min_k = 256)
 {
     if (!(std::is_same<T, double>::value || std::is_same<T, cxd>::value))
         return false;
     if (hemm_tma_disabled() || get_encode_fn() == nullptr)
         return false;
     const int64_t per16 = 16 / (int64_t)sizeof(T) > 0 ? 16 / (int64_t)sizeof(T) : 1; // elements per 16 B
-    if (M < 256 || K < 256 || k < 8)
+    if (M < min_m || K < min_k || k < 8)
         return false; // tiny problems: launch-bound anyway
     if (lda % per16 || ldb % per16 || ldc % per16)
         return false;

@@ -43,6 +43,11 @@ struct HemmProfile
 HemmProfile g_hprof;
 
 template <class T>
+int hemm_rect_impl(int ta, int64_t M, int64_t K, int64_t k, double are, double aim, const void* A, int64_t lda,
+                   const void* B, int64_t ldb, double bre, double bim, void* C, int64_t ldc, double shift,
+                   const double* theta, void* stream);
+
+template <class T>
 int gemm_impl(int ta, int tb, int64_t M, int64_t N, int64_t K, double are, double aim, const void* A, int64_t lda,
               const void* B, int64_t ldb, double bre, double bim, void* C, int64_t ldc, int uplo, void* ws,
               size_t ws_bytes, void* stream)
@@ -50,6 +55,18 @@ int gemm_impl(int ta, int tb, int64_t M, int64_t N, int64_t K, double are, doubl
     using C_ = typename Traits<T>::comp;
     if (M < 0 || N < 0 || K < 0)
         return -2;
+    // Tall products with a K-major right operand (Q Z, (A Q) Z, the TRSM block updates, W^H Q when it has enough
+    // tiles) run on the TMA + DMMA pipeline of the filter kernel; narrow / deep Gram products stay on the split-K
+    // path below.
+    if constexpr (std::is_same<T, double>::value || std::is_same<T, cxd>::value)
+    {
+        constexpr int BN = HemmCfg<Traits<T>::cplx>::BN;
+        const int64_t tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
+        if (tb == 0 && uplo == 0 && M >= 128 && K >= 64 && N >= 8 && tiles >= 96 &&
+            hemm_tma_supported<T>(M, K, N, A, lda, B, ldb, C, ldc, 128, 64))
+            return hemm_tma_launch<T>(ta != 0, M, K, N, make_comp<C_>(are, aim), (const T*)A, lda, (const T*)B, ldb,
+                                      make_comp<C_>(bre, bim), (T*)C, ldc, 0.0, nullptr, S(stream));
+    }
     GemmArgs<T> p{};
     p.M = M;
     p.N = N;
@@ -206,39 +223,17 @@ int trsm_impl(int64_t rows, int64_t n, const void* Rv, int64_t ldr, void* Vv, in
     {
         const int64_t j0 = b * TRSM_NB;
         const int64_t nb = std::min<int64_t>(TRSM_NB, n - j0);
-        GemmArgs<T> p{};
         if (b > 0)
         {
             // V_b -= X[:, :j0] R[:j0, j0:j0+nb]
-            p.M = rows;
-            p.N = nb;
-            p.K = j0;
-            p.A = X;
-            p.lda = ldx;
-            p.B = Rm + j0 * ldr;
-            p.ldb = ldr;
-            p.C = V + j0 * ldv;
-            p.ldc = ldv;
-            p.alpha = from_real<C_>(-1.0);
-            p.beta = from_real<C_>(1.0);
-            int rc = gemm_launch<T>(false, false, p, nullptr, 0, st);
+            int rc = gemm_impl<T>(0, 0, rows, nb, j0, -1.0, 0.0, X, ldx, Rm + j0 * ldr, ldr, 1.0, 0.0, V + j0 * ldv, ldv,
+                                  0, nullptr, 0, stream);
             if (rc)
                 return rc;
         }
         // X_b = V_b inv(R_bb)
-        GemmArgs<T> q{};
-        q.M = rows;
-        q.N = nb;
-        q.K = nb;
-        q.A = V + j0 * ldv;
-        q.lda = ldv;
-        q.B = Rinv + b * TRSM_NB * TRSM_NB;
-        q.ldb = TRSM_NB;
-        q.C = X + j0 * ldx;
-        q.ldc = ldx;
-        q.alpha = from_real<C_>(1.0);
-        q.beta = czero<C_>();
-        int rc = gemm_launch<T>(false, false, q, nullptr, 0, st);
+        int rc = gemm_impl<T>(0, 0, rows, nb, nb, 1.0, 0.0, V + j0 * ldv, ldv, Rinv + b * TRSM_NB * TRSM_NB, TRSM_NB, 0.0,
+                              0.0, X + j0 * ldx, ldx, 0, nullptr, 0, stream);
         if (rc)
             return rc;
     }
@@ -456,7 +451,8 @@ int gemv_impl(int64_t rows, int64_t cols, const void* A, int64_t lda, const void
     cudaStream_t st = S(stream);
     if (rows <= 0 || cols <= 0 || nv <= 0)
         return 0;
-    const int blocks = (int)std::min<int64_t>((cols + 7) / 8, 148 * 8);
+    // one warp per GEMV_CJ columns, 8 warps per block
+    const int blocks = (int)std::min<int64_t>((cols + 8 * GEMV_CJ - 1) / (8 * GEMV_CJ), 148 * 8);
     int v = 0;
     while (v < nv)
     {
