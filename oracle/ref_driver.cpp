@@ -20,6 +20,13 @@
 //   chase_ref_cpu_<d|z|s|c> --N n --nev k --nex x --matrix clement|uniform|uniform_dense|file:<path>
 //        [--tol t] [--deg d] [--opt 0|1] [--maxiter i] [--seq k] [--perturb p]
 //        [--vecs file] [--out result.json] [--dump-eigvecs file] [--initvecs-only file]
+//        [--numlanczos n] [--lanczositer m]
+//
+// Built with -DREF_PSEUDO (chase_ref_cpu_p<z|c>) the backend is
+// ChASECPU<T, PseudoHermitianMatrix<T>> driven by chase::Solve_pseudo
+// (algorithm/algorithm.hpp:359): V holds 2 (nev+nex) columns, --matrix must be
+// file:<path> (e.g. the reference's tests/linalg/internal/BSE_matrices/*.bin
+// or a matrix written by oracle/chase_oracle.py: bse_matrix).
 #include <chrono>
 #include <complex>
 #include <cstdio>
@@ -50,162 +57,7 @@ struct is_cplx<std::complex<U>> : std::true_type
 {
 };
 
-static std::string fmt(double v)
-{
-    char buf[64];
-    std::snprintf(buf, sizeof buf, "%.17g", v);
-    return buf;
-}
-
-// Forwards every virtual to the wrapped reference backend and logs the call.
-template <class S>
-class TraceBackend : public chase::ChaseBase<S>
-{
-    using B = chase::Base<S>;
-
-public:
-    explicit TraceBackend(chase::ChaseBase<S>* inner) : in_(inner) {}
-    std::vector<std::string> calls;
-    std::size_t swaps = 0, hemm_cols = 0, hemm_calls = 0;
-
-    void Shift(S c, bool un = false) override
-    {
-        calls.push_back("Shift " + fmt(std::real(c)) + (un ? " 1" : " 0"));
-        in_->Shift(c, un);
-    }
-    void HEMM(std::size_t nev, S a, S b, std::size_t ol,
-              std::size_t orr = 0) override
-    {
-        calls.push_back("HEMM " + std::to_string(nev) + " " +
-                        fmt(std::real(a)) + " " + fmt(std::real(b)) + " " +
-                        std::to_string(ol) + " " + std::to_string(orr));
-        hemm_calls++;
-        hemm_cols += nev - orr;
-        in_->HEMM(nev, a, b, ol, orr);
-    }
-    void HEMM_H2(std::size_t nev, S a, S b, S g, std::size_t ol,
-                 std::size_t orr = 0) override
-    {
-        in_->HEMM_H2(nev, a, b, g, ol, orr);
-    }
-    void ApplyKconjugate(std::size_t b) override { in_->ApplyKconjugate(b); }
-    void FilterPhaseStart() override { in_->FilterPhaseStart(); }
-    void FilterPhaseEnd() override { in_->FilterPhaseEnd(); }
-    void QR(std::size_t f, B cond) override
-    {
-        calls.push_back("QR " + std::to_string(f) + " " + fmt(cond));
-        in_->QR(f, cond);
-    }
-    void RR(B* ritzv, std::size_t block) override
-    {
-        in_->RR(ritzv, block);
-        std::string s = "RR " + std::to_string(block);
-        calls.push_back(s);
-        std::string v = "RITZV";
-        for (std::size_t i = 0; i < block; ++i)
-            v += " " + fmt(ritzv[i]);
-        calls.push_back(v);
-    }
-    void Sort(B* a, B* b, B* c) override { in_->Sort(a, b, c); }
-    void Resd(B* ritzv, B* resd, std::size_t f) override
-    {
-        in_->Resd(ritzv, resd, f);
-        std::size_t nevex = in_->GetNev() + in_->GetNex();
-        std::string v = "RESID " + std::to_string(f);
-        for (std::size_t i = 0; i + f < nevex; ++i)
-            v += " " + fmt(resd[i]);
-        calls.push_back(v);
-    }
-    void Lanczos(std::size_t m, B* ub) override
-    {
-        in_->Lanczos(m, ub);
-        calls.push_back("Lanczos1 " + std::to_string(m) + " " + fmt(*ub));
-    }
-    void Lanczos(std::size_t M, std::size_t nv, B* ub, B* rv, B* tau,
-                 B* rV) override
-    {
-        in_->Lanczos(M, nv, ub, rv, tau, rV);
-        std::string s = "Lanczos " + std::to_string(M) + " " +
-                        std::to_string(nv) + " " + fmt(*ub);
-        calls.push_back(s);
-        std::string t = "THETA";
-        for (std::size_t i = 0; i < M * nv; ++i)
-            t += " " + fmt(rv[i]);
-        calls.push_back(t);
-        t = "TAU";
-        for (std::size_t i = 0; i < M * nv; ++i)
-            t += " " + fmt(tau[i]);
-        calls.push_back(t);
-    }
-    void LanczosDos(std::size_t idx, std::size_t m, S* rvc) override
-    {
-        calls.push_back("LanczosDos " + std::to_string(idx) + " " +
-                        std::to_string(m));
-        in_->LanczosDos(idx, m, rvc);
-    }
-    void Swap(std::size_t i, std::size_t j) override
-    {
-        swaps++;
-        in_->Swap(i, j);
-    }
-    void Lock(std::size_t n) override
-    {
-        calls.push_back("Lock " + std::to_string(n) + " swaps " +
-                        std::to_string(swaps));
-        in_->Lock(n);
-    }
-    bool checkSymmetryEasy() override { return in_->checkSymmetryEasy(); }
-    bool isSym() override { return in_->isSym(); }
-    bool checkPseudoHermicityEasy() override
-    {
-        return in_->checkPseudoHermicityEasy();
-    }
-    bool isPseudoHerm() override { return in_->isPseudoHerm(); }
-    void symOrHermMatrix(char u) override { in_->symOrHermMatrix(u); }
-    void Start() override
-    {
-        calls.push_back("Start");
-        in_->Start();
-    }
-    void End() override
-    {
-        calls.push_back("End swaps " + std::to_string(swaps));
-        in_->End();
-    }
-    void initVecs(bool random) override
-    {
-        calls.push_back(std::string("initVecs ") + (random ? "1" : "0"));
-        in_->initVecs(random);
-    }
-    std::size_t GetN() const override { return in_->GetN(); }
-    std::size_t GetNev() override { return in_->GetNev(); }
-    std::size_t GetNex() override { return in_->GetNex(); }
-    std::size_t GetLanczosIter() override { return in_->GetLanczosIter(); }
-    std::size_t GetNumLanczos() override { return in_->GetNumLanczos(); }
-    std::size_t GetRitzvBlockSize() const override
-    {
-        return in_->GetRitzvBlockSize();
-    }
-    B* GetRitzv() override { return in_->GetRitzv(); }
-    B* GetResid() override { return in_->GetResid(); }
-    chase::ChaseConfig<S>& GetConfig() override { return in_->GetConfig(); }
-    int get_nprocs() override { return in_->get_nprocs(); }
-    int get_rank() override { return in_->get_rank(); }
-    void set_early_locked_residuals(std::vector<B> v) override
-    {
-        calls.push_back("early_locked " + std::to_string(v.size()));
-        in_->set_early_locked_residuals(v);
-    }
-#ifdef CHASE_OUTPUT
-    void Output(chase::LogLevel l, std::string s,
-                const char* c = "algorithm") override
-    {
-        in_->Output(l, s, c);
-    }
-#endif
-private:
-    chase::ChaseBase<S>* in_;
-};
+#include "trace_backend.hpp"
 
 template <typename U>
 static U cj_(const U& x) { return x; }
@@ -272,7 +124,7 @@ int main(int argc, char** argv)
     std::size_t N = 1001, nev = 100, nex = 40, maxiter = 25, seq = 1;
     std::string matrix = "clement", out, dump_vecs, vecs_in, initvecs_only;
     double tol = -1, perturb = 1e-4;
-    long deg = -1;
+    long deg = -1, numlanczos = -1, lanczositer = -1;
     int opt = 1;
     for (int i = 1; i + 1 < argc; i += 2)
     {
@@ -291,6 +143,8 @@ int main(int argc, char** argv)
         else if (a == "--dump-eigvecs") dump_vecs = v;
         else if (a == "--vecs") vecs_in = v;
         else if (a == "--initvecs-only") initvecs_only = v;
+        else if (a == "--numlanczos") numlanczos = std::stol(v);
+        else if (a == "--lanczositer") lanczositer = std::stol(v);
         else
         {
             std::cerr << "unknown arg " << a << "\n";
@@ -298,8 +152,15 @@ int main(int argc, char** argv)
         }
     }
     const std::size_t nevex = nev + nex;
-    std::vector<T> V(N * nevex), H(N * N, T(0));
-    std::vector<R> Lambda(nevex);
+#ifdef REF_PSEUDO
+    const std::size_t ncols = 2 * nevex; // [positive | K-conjugate] halves
+    using Backend = chase::Impl::ChASECPU<T, chase::matrix::PseudoHermitianMatrix<T>>;
+#else
+    const std::size_t ncols = nevex;
+    using Backend = chase::Impl::ChASECPU<T>;
+#endif
+    std::vector<T> V(N * ncols), H(N * N, T(0));
+    std::vector<R> Lambda(ncols);
 
     if (matrix == "clement")
     {
@@ -334,26 +195,27 @@ int main(int argc, char** argv)
         return 2;
     }
 
-    chase::Impl::ChASECPU<T> single(N, nev, nex, H.data(), N, V.data(), N,
-                                    Lambda.data());
+    Backend single(N, nev, nex, H.data(), N, V.data(), N, Lambda.data());
     auto& config = single.GetConfig();
     if (tol > 0) config.SetTol(tol);
     if (deg > 0) config.SetDeg(deg);
     config.SetOpt(opt != 0);
     config.SetMaxIter(maxiter);
     config.SetApprox(false);
+    if (numlanczos > 0) config.SetNumLanczos(numlanczos);
+    if (lanczositer > 0) config.SetLanczosIter(lanczositer);
 
     if (!initvecs_only.empty())
     {
         single.initVecs(true);
         std::ofstream f(initvecs_only, std::ios::binary);
-        f.write(reinterpret_cast<char*>(V.data()), sizeof(T) * N * nevex);
+        f.write(reinterpret_cast<char*>(V.data()), sizeof(T) * N * ncols);
         return 0;
     }
     if (!vecs_in.empty())
     {
         std::ifstream f(vecs_in, std::ios::binary);
-        f.read(reinterpret_cast<char*>(V.data()), sizeof(T) * N * nevex);
+        f.read(reinterpret_cast<char*>(V.data()), sizeof(T) * N * ncols);
         config.SetApprox(true);
     }
 
@@ -365,6 +227,10 @@ int main(int argc, char** argv)
        << "\", \"N\": " << N << ", \"nev\": " << nev << ", \"nex\": " << nex
        << ", \"matrix\": \"" << matrix << "\", \"tol\": " << fmt(config.GetTol())
        << ", \"deg\": " << config.GetDeg() << ", \"opt\": " << opt
+#ifdef REF_PSEUDO
+       << ", \"pseudo\": 1, \"numlanczos\": " << config.GetNumLanczos()
+       << ", \"lanczositer\": " << config.GetLanczosIter()
+#endif
        << ", \"problems\": [";
 
     for (std::size_t idx = 0; idx < seq; ++idx)
@@ -372,7 +238,11 @@ int main(int argc, char** argv)
         chase::PerformanceDecoratorChase<T> perf(&single);
         TraceBackend<T> trace(&perf);
         auto t0 = std::chrono::high_resolution_clock::now();
+#ifdef REF_PSEUDO
+        chase::Solve_pseudo(&trace);
+#else
         chase::Solve(&trace);
+#endif
         auto t1 = std::chrono::high_resolution_clock::now();
         auto& pd = perf.GetPerfData();
         // print() is the only public path that folds the time points into
@@ -436,7 +306,7 @@ int main(int argc, char** argv)
     if (!dump_vecs.empty())
     {
         std::ofstream f(dump_vecs, std::ios::binary);
-        f.write(reinterpret_cast<char*>(V.data()), sizeof(T) * N * nevex);
+        f.write(reinterpret_cast<char*>(V.data()), sizeof(T) * N * ncols);
     }
     return 0;
 }

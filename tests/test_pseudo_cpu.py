@@ -1,0 +1,139 @@
+"""CPU checks of the pseudo-Hermitian (BSE) path's test infrastructure and host driver.
+
+* the numpy restatements of the backend arithmetic (oracle/chase_oracle.py: rayleigh_ritz_v2, lanczos_pseudo,
+  k_conjugate, ...) against the reference's golden spectra (tests/golden/bse_fixtures/eigs_*.bin, copied from
+  /root/reference/tests/linalg/internal/BSE_matrices/);
+* the golden traces of the unmodified reference solver (chase_ref_cpu_p{z,c}, Solve_pseudo) against those spectra;
+* the NEW C++ driver (chase_b200/host/algorithm.hpp: solve_pseudo, solve) against the reference's own driver on the
+  reference CPU backend — bit-identical call traces (oracle/xcheck_driver.cpp; only where oracle/_ref was built,
+  i.e. in the build container)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import chase_oracle as co
+from tests.golden_util import GOLDEN, load, parse_trace
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BSE = os.path.join(GOLDEN, "bse_fixtures")
+
+
+def _fixture(name, dt, n):
+    return np.asfortranarray(np.fromfile(os.path.join(BSE, name), dtype=dt).reshape(n, n).T)
+
+
+def _eigs(name, dt):
+    return np.fromfile(os.path.join(BSE, name), dtype=dt).real.astype(np.float64)
+
+
+def test_fixture_is_pseudo_hermitian():
+    H = _fixture("cdouble_random_BSE.bin", np.complex128, 200)
+    SH = co.flip_lower_half(H)
+    assert np.abs(SH - SH.conj().T).max() < 1e-12
+    assert np.linalg.eigvalsh(SH).min() > 0
+
+
+@pytest.mark.parametrize("mat,eig,dt,n,tol", [
+    ("cdouble_random_BSE.bin", "eigs_cdouble_random_BSE.bin", np.complex128, 200, 1e-11),
+    ("cdouble_tiny_random_BSE.bin", "eigs_cdouble_tiny_random_BSE.bin", np.complex128, 10, 1e-12),
+])
+def test_rayleigh_ritz_v2_reproduces_golden_spectrum(mat, eig, dt, n, tol):
+    """Full-space projection: rayleighRitz_v2 must return the complete spectrum, positives first (ascending)."""
+    H = _fixture(mat, dt, n)
+    e = _eigs(eig, dt)
+    r, V = co.rayleigh_ritz_v2(H, np.eye(n, dtype=dt))
+    pos = np.sort(e[e > 0])
+    assert np.max(np.abs(r[: n // 2] - pos) / pos) < tol
+    assert np.max(np.abs(np.sort(r[n // 2:]) - np.sort(e[e < 0]))) < tol * np.abs(e).max()
+    assert np.linalg.norm(H @ V - V * r[: n // 2], axis=0).max() < 1e-10 * np.abs(e).max()
+    # K-conjugates are eigenvectors of the mirrored eigenvalues
+    K = co.k_conjugate(V)
+    assert np.linalg.norm(H @ K + K * r[: n // 2], axis=0).max() < 1e-10 * np.abs(e).max()
+
+
+def test_synthetic_bse_matrix_has_the_stated_spectrum():
+    H, lam = co.bse_matrix(300)
+    ev = np.sort(np.linalg.eigvals(H).real)
+    assert np.max(np.abs(ev[150:] - lam)) < 1e-10
+    assert np.max(np.abs(ev[:150] + lam[::-1])) < 1e-10
+    SH = co.flip_lower_half(H)
+    assert np.abs(SH - SH.conj().T).max() < 1e-13 and np.linalg.eigvalsh(SH).min() > 0
+
+
+def test_lanczos_pseudo_ritz_values_inside_spectrum_and_weights_normalised():
+    H = _fixture("cdouble_random_BSE.bin", np.complex128, 200)
+    e = _eigs("eigs_cdouble_random_BSE.bin", np.complex128)
+    V = co.init_vectors(200, 80, np.complex128)
+    Th, Tau, rV, d, ee = co.lanczos_pseudo(H, V, 24, 4)
+    assert np.all(np.abs(Th) <= np.abs(e).max() * (1 + 1e-10))
+    assert np.allclose(Tau.reshape(4, 24).sum(axis=1), 1.0)
+    # the golden trace of the reference (same start block after its QR) has the same extreme Ritz value scale
+    g = load("pseudo_bse_z_N200_dflt")
+    ref = parse_trace(g["problems"][0]["trace"])
+    assert ref["lanczos"][0] == 24 and ref["lanczos"][1] == 4
+    assert np.abs(ref["theta"]).max() <= np.abs(e).max() * (1 + 1e-10)
+
+
+def test_qr_pseudo_keeps_locked_and_s_orthogonalises_active():
+    rng = np.random.default_rng(3)
+    N, ncols, locked = 120, 24, 4
+    V = np.asfortranarray(rng.standard_normal((N, ncols)) + 1j * rng.standard_normal((N, ncols)))
+    Q = co.qr_pseudo(V, locked)
+    act = Q[:, locked:ncols - locked]
+    lock = np.hstack([Q[:, :locked], Q[:, ncols - locked:]])
+    assert np.array_equal(lock, np.hstack([V[:, :locked], V[:, ncols - locked:]]))
+    assert np.linalg.norm(act.conj().T @ act - np.eye(ncols - 2 * locked)) < 1e-12
+    assert np.linalg.norm(co.flip_lower_half(lock).conj().T @ act) < 1e-12
+
+
+@pytest.mark.parametrize("name,eig,dt,tol", [
+    ("pseudo_bse_z_N200", "eigs_cdouble_random_BSE.bin", np.complex128, 1e-10),
+    ("pseudo_bse_z_N200_dflt", "eigs_cdouble_random_BSE.bin", np.complex128, 1e-10),
+    ("pseudo_bse_c_N200", "eigs_cfloat_random_BSE.bin", np.complex64, 1e-4),
+])
+def test_reference_golden_trace_matches_golden_spectrum(name, eig, dt, tol):
+    """The reference solver's smallest positive eigenvalues (golden trace) agree with the reference's own spectra."""
+    g = load(name)
+    p = g["problems"][0]
+    e = _eigs(eig, dt)
+    pos = np.sort(e[e > 0])[: g["nev"]]
+    got = np.array(p["ritzv"][: g["nev"]])
+    assert np.max(np.abs(got - pos) / pos) < tol
+    assert np.all(np.array(p["resid"][: g["nev"]]) < 1000 * g["tol"])  # early locking: < 1000 tol (algorithm.inc:752)
+
+
+def test_reference_golden_trace_synthetic_known_answer():
+    g = load("pseudo_synth_z_N600")
+    _, lam = co.bse_matrix(600, seed=int(g["matrix"].split(":")[1]))
+    got = np.array(g["problems"][0]["ritzv"][: g["nev"]])
+    assert np.max(np.abs(got - lam[: g["nev"]]) / lam[: g["nev"]]) < 1e-10
+
+
+XCHECK = [
+    ("xcheck_d", ["--N", "256", "--nev", "24", "--nex", "16", "--deg", "16"]),
+    ("xcheck_z", ["--N", "300", "--nev", "30", "--nex", "20"]),
+    ("xcheck_d", ["--N", "300", "--nev", "30", "--nex", "10", "--opt", "0"]),
+    ("xcheck_pz", ["--N", "200", "--nev", "20", "--nex", "20", "--numlanczos", "10", "--lanczositer", "40",
+                   "--matrix", "file:" + os.path.join(BSE, "cdouble_random_BSE.bin")]),
+    ("xcheck_pz", ["--N", "200", "--nev", "20", "--nex", "10",
+                   "--matrix", "file:" + os.path.join(BSE, "cdouble_random_BSE.bin")]),
+    ("xcheck_pz", ["--N", "200", "--nev", "30", "--nex", "10", "--opt", "0",
+                   "--matrix", "file:" + os.path.join(BSE, "cdouble_random_BSE.bin")]),
+    ("xcheck_pc", ["--N", "200", "--nev", "20", "--nex", "20", "--tol", "1e-5", "--deg", "10",
+                   "--matrix", "file:" + os.path.join(BSE, "cfloat_random_BSE.bin")]),
+]
+
+
+@pytest.mark.parametrize("exe,args", XCHECK)
+def test_new_driver_is_call_identical_to_reference_driver(exe, args):
+    path = os.path.join(ROOT, "oracle", "_ref", exe)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (needs /root/reference; built by __graft_entry__.build() in the container)")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+    out = subprocess.run([path] + args, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    j = json.loads(out.stdout)
+    assert j["identical"] is True and j["iterations"] >= 1
