@@ -261,6 +261,108 @@ __global__ void __launch_bounds__(1024) lanczos_step_kernel(long long rows, int 
     }
 }
 
+// ---- pseudo-Hermitian (BSE) helpers ------------------------------------------------------------------------------
+// H = [[A, B], [-conj(B), -conj(A)]], S = diag(I, -I).  Reference counterparts: flipSign.cu (S X), conjugate.cu +
+// lacpy (K-conjugation, Impl/chase_gpu/chase_gpu.hpp:718-742), pseudo_hermitian_lanczos_diag.cu and the S-inner-
+// product Lanczos of linalg/internal/cuda/lanczos.hpp:547-785 (CPU statement: cpu/lanczos.hpp:332-516).
+
+// X[i, j] *= a for i < nrows, j < cols (X already points at the first row to scale): a = -1 on the lower half is
+// S X (flipLowerHalfMatrixSign), a = 1e-3 is the start-vector damping scaleLowerBlockRows (chase_gpu.hpp:518-529)
+template <class T>
+__global__ void scale_rows_kernel(long long nrows, long long cols, T* X, long long ldx, double a)
+{
+    using C = typename Traits<T>::comp;
+    for (long long j = blockIdx.y; j < cols; j += gridDim.y)
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nrows;
+             i += (long long)gridDim.x * blockDim.x)
+            X[i + j * ldx] = narrow<T>(cmul(a, (C)widen(X[i + j * ldx])));
+}
+
+// K-conjugate partner vectors: dst[:, j] = conj([src[half:2 half, j]; src[0:half, j]])  (src and dst: disjoint columns)
+template <class T>
+__global__ void kconj_kernel(long long half, long long cols, const T* src, long long lds, T* dst, long long ldd)
+{
+    using C = typename Traits<T>::comp;
+    for (long long j = blockIdx.y; j < cols; j += gridDim.y)
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < half;
+             i += (long long)gridDim.x * blockDim.x)
+        {
+            const C up = (C)widen(src[i + j * lds]), lo = (C)widen(src[i + half + j * lds]);
+            dst[i + half + j * ldd] = narrow<T>(cconj(up));
+            dst[i + j * ldd] = narrow<T>(cconj(lo));
+        }
+}
+
+// S-inner-product normalisation of one Lanczos vector (blockIdx.x): with v2 = H v1,
+//   beta = sqrt(Re <v1, S v2>);  v1 /= beta;  v2 /= beta;  e[ke] = beta (ke >= 0);  bnorm[vi] = beta
+template <class T>
+__global__ void __launch_bounds__(1024) lanczos_pseudo_norm_kernel(long long rows, long long half, int ke, int M,
+                                                                    T* v1, T* v2, long long ld, double* e,
+                                                                    double* bnorm)
+{
+    using C = typename Traits<T>::comp;
+    using R = typename Traits<T>::real;
+    __shared__ double sh[32];
+    const int vi = blockIdx.x;
+    T* x1 = v1 + (long long)vi * ld;
+    T* x2 = v2 + (long long)vi * ld;
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+    {
+        const double t = creal(cmul(cconj((C)widen(x1[i])), (C)widen(x2[i])));
+        acc += (i < half) ? t : -t;
+    }
+    acc = block_sum(acc, sh);
+    const R beta = (R)sqrt(acc);
+    if (threadIdx.x == 0)
+    {
+        bnorm[vi] = (double)beta;
+        if (ke >= 0)
+            e[ke + (long long)M * vi] = (double)beta;
+    }
+    const double inv = (double)(R)(1 / beta);
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+    {
+        x1[i] = narrow<T>(cmul(inv, (C)widen(x1[i])));
+        x2[i] = narrow<T>(cmul(inv, (C)widen(x2[i])));
+    }
+}
+
+// One pseudo-Hermitian Lanczos step for vector blockIdx.x (v1, v2 already S-normalised):
+//   alpha = <v2, S v2> (real);  v2 -= alpha v1;  d[k] = alpha;  if 0 < k < M-1: v2 -= beta_k v0
+template <class T>
+__global__ void __launch_bounds__(1024) lanczos_pseudo_step_kernel(long long rows, long long half, int k, int M,
+                                                                    const T* v0, const T* v1, T* v2, long long ld,
+                                                                    double* d, const double* bnorm)
+{
+    using C = typename Traits<T>::comp;
+    using R = typename Traits<T>::real;
+    __shared__ double sh[32];
+    const int vi = blockIdx.x;
+    const T* x0 = v0 + (long long)vi * ld;
+    const T* x1 = v1 + (long long)vi * ld;
+    T* x2 = v2 + (long long)vi * ld;
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+    {
+        const double t = cabs2(widen(x2[i]));
+        acc += (i < half) ? t : -t;
+    }
+    acc = block_sum(acc, sh);
+    const double alpha = (double)(R)acc;
+    if (threadIdx.x == 0)
+        d[k + (long long)M * vi] = alpha;
+    const bool with_v0 = (k > 0 && k < M - 1);
+    const double beta = with_v0 ? (double)(R)bnorm[vi] : 0.0;
+    for (long long i = threadIdx.x; i < rows; i += blockDim.x)
+    {
+        C w = csub((C)widen(x2[i]), cmul(alpha, (C)widen(x1[i])));
+        if (with_v0)
+            w = csub(w, cmul(beta, (C)widen(x0[i])));
+        x2[i] = narrow<T>(w);
+    }
+}
+
 // ---- Philox4x32-10 + Box-Muller: production-mode start vectors ----------------
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2])
 {

@@ -673,6 +673,47 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
         herm_mirror_kernel<TT><<<1184, 256, 0, kcount(S(st))>>>(n, (TT*)A, lda, from_upper);                                  \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_scale_rows_##X(int64_t nrows, int64_t cols, void* Xm, int64_t ldx, double a, void* st)  \
+    {                                                                                                                  \
+        if (nrows <= 0 || cols <= 0)                                                                                   \
+            return 0;                                                                                                  \
+        scale_rows_kernel<TT><<<grid2d(nrows, cols), 256, 0, kcount(S(st))>>>(nrows, cols, (TT*)Xm, ldx, a);          \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_kconj_##X(int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst,          \
+                                        int64_t ldd, void* st)                                                        \
+    {                                                                                                                  \
+        if (rows % 2 != 0)                                                                                             \
+            return -2;                                                                                                 \
+        if (rows <= 0 || cols <= 0)                                                                                    \
+            return 0;                                                                                                  \
+        kconj_kernel<TT><<<grid2d(rows / 2, cols), 256, 0, kcount(S(st))>>>(rows / 2, cols, (const TT*)src, lds,      \
+                                                                            (TT*)dst, ldd);                            \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_lanczos_pseudo_norm_##X(int64_t rows, int nv, int ke, int M, void* v1, void* v2,        \
+                                                      int64_t ld, double* e, double* bnorm, void* st)                 \
+    {                                                                                                                  \
+        if (nv <= 0)                                                                                                   \
+            return 0;                                                                                                  \
+        lanczos_pseudo_norm_kernel<TT><<<nv, 1024, 0, kcount(S(st))>>>(rows, rows / 2, ke, M, (TT*)v1, (TT*)v2, ld,   \
+                                                                       e, bnorm);                                      \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_lanczos_pseudo_step_##X(int64_t rows, int nv, int k, int M, const void* v0,             \
+                                                      const void* v1, void* v2, int64_t ld, double* d,                \
+                                                      const double* bnorm, void* st)                                  \
+    {                                                                                                                  \
+        if (nv <= 0)                                                                                                   \
+            return 0;                                                                                                  \
+        lanczos_pseudo_step_kernel<TT><<<nv, 1024, 0, kcount(S(st))>>>(rows, rows / 2, k, M, (const TT*)v0,           \
+                                                                       (const TT*)v1, (TT*)v2, ld, d, bnorm);          \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
     }
 
 CB2_DEFINE_API(s, float)

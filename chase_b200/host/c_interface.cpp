@@ -57,7 +57,10 @@ void run_solve(Backend* solver, std::size_t N, int deg, chase::Base<T> tol, char
     g_last.error.clear();
     try
     {
-        chase::Solve(&perf);
+        if (solver->isPseudoHerm())
+            chase::Solve_pseudo(&perf); // reference ChASE_SEQ_Solve, chase_c_interface.cpp:461-466
+        else
+            chase::Solve(&perf);
     }
     catch (const std::exception& e)
     {
@@ -101,11 +104,15 @@ void run_solve(Backend* solver, std::size_t N, int deg, chase::Base<T> tol, char
         pd.print(N, factor);
 }
 
-template <class T>
+// MT = chase::matrix::PseudoHermitianMatrix<T>: the ?chase_init_pseudo_ singletons (reference
+// chase_c_interface.cpp:249-320); V then has 2 (nev+nex) columns and ritzv 2 (nev+nex) entries.
+template <class T, class MT = chase::matrix::Matrix<T, chase::platform::GPU>>
 struct Seq
 {
     using R = chase::Base<T>;
-    std::unique_ptr<chase::Impl::ChASEGPU<T>> solver;
+    static constexpr std::size_t kWidth =
+        std::is_same<MT, chase::matrix::PseudoHermitianMatrix<T, chase::platform::GPU>>::value ? 2 : 1;
+    std::unique_ptr<chase::Impl::ChASEGPU<T, MT>> solver;
     std::vector<T> vec;   // internal V when the caller passed NULL
     std::vector<R> ritz;  // internal ritzv when the caller passed NULL
     T* V = nullptr;
@@ -124,19 +131,19 @@ struct Seq
         V = V_;
         if (V == nullptr)
         {
-            vec.assign((std::size_t)N_ * (std::size_t)(nev + nex), T(0));
+            vec.assign((std::size_t)N_ * kWidth * (std::size_t)(nev + nex), T(0));
             V = vec.data();
         }
         ritzv = ritzv_;
         if (ritzv == nullptr)
         {
-            ritz.assign((std::size_t)(nev + nex), R(0));
+            ritz.assign(kWidth * (std::size_t)(nev + nex), R(0));
             ritzv = ritz.data();
         }
         try
         {
-            solver.reset(new chase::Impl::ChASEGPU<T>((std::size_t)N_, (std::size_t)nev, (std::size_t)nex, H,
-                                                      (std::size_t)ldh, V, (std::size_t)N_, ritzv));
+            solver.reset(new chase::Impl::ChASEGPU<T, MT>((std::size_t)N_, (std::size_t)nev, (std::size_t)nex, H,
+                                                          (std::size_t)ldh, V, (std::size_t)N_, ritzv));
         }
         catch (const std::exception& e)
         {
@@ -264,6 +271,8 @@ using SD = Seq<double>;
 using SS = Seq<float>;
 using SZ = Seq<std::complex<double>>;
 using SC = Seq<std::complex<float>>;
+using SZP = Seq<std::complex<double>, chase::matrix::PseudoHermitianMatrix<std::complex<double>, chase::platform::GPU>>;
+using SCP = Seq<std::complex<float>, chase::matrix::PseudoHermitianMatrix<std::complex<float>, chase::platform::GPU>>;
 using PD = Dist<double>;
 using PS = Dist<float>;
 using PZ = Dist<std::complex<double>>;
@@ -280,6 +289,10 @@ void with_active_config(F&& f)
         f(SZ::get().solver->GetConfig());
     else if (SC::get().solver)
         f(SC::get().solver->GetConfig());
+    else if (SZP::get().solver)
+        f(SZP::get().solver->GetConfig());
+    else if (SCP::get().solver)
+        f(SCP::get().solver->GetConfig());
     else if (PD::get().solver)
         f(PD::get().solver->GetConfig());
     else if (PS::get().solver)
@@ -343,6 +356,26 @@ extern "C"
         *init = SZ::get().init(*N, *nev, *nex, reinterpret_cast<cd*>(H), *ldh, nullptr, nullptr);
     }
 
+    // pseudo-Hermitian (BSE) singletons, reference chase_c_interface.h:42-58
+    void cchase_init_pseudo_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, CHASE_B200_CF* V, float* ritzv,
+                             int* init)
+    {
+        *init = SCP::get().init(*N, *nev, *nex, reinterpret_cast<cf*>(H), *ldh, reinterpret_cast<cf*>(V), ritzv);
+    }
+    void zchase_init_pseudo_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, CHASE_B200_CD* V, double* ritzv,
+                             int* init)
+    {
+        *init = SZP::get().init(*N, *nev, *nex, reinterpret_cast<cd*>(H), *ldh, reinterpret_cast<cd*>(V), ritzv);
+    }
+    void cchase_init_pseudo_internal_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, int* init)
+    {
+        *init = SCP::get().init(*N, *nev, *nex, reinterpret_cast<cf*>(H), *ldh, nullptr, nullptr);
+    }
+    void zchase_init_pseudo_internal_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, int* init)
+    {
+        *init = SZP::get().init(*N, *nev, *nex, reinterpret_cast<cd*>(H), *ldh, nullptr, nullptr);
+    }
+
     void dchase_finalize_(int* flag)
     {
         SD::get().finalize();
@@ -356,11 +389,13 @@ extern "C"
     void cchase_finalize_(int* flag)
     {
         SC::get().finalize();
+        SCP::get().finalize();
         *flag = 0;
     }
     void zchase_finalize_(int* flag)
     {
         SZ::get().finalize();
+        SZP::get().finalize();
         *flag = 0;
     }
 
@@ -372,13 +407,28 @@ extern "C"
     {
         SS::get().solve(*deg, *tol, *mode, *opt, *qr);
     }
+    // the pseudo-Hermitian singleton takes the call when it exists (reference chase_c_interface.cpp:2204-2231)
     void zchase_(int* deg, double* tol, char* mode, char* opt, char* qr)
     {
-        SZ::get().solve(*deg, *tol, *mode, *opt, *qr);
+        if (SZP::get().solver)
+            SZP::get().solve(*deg, *tol, *mode, *opt, *qr);
+        else
+            SZ::get().solve(*deg, *tol, *mode, *opt, *qr);
     }
     void cchase_(int* deg, float* tol, char* mode, char* opt, char* qr)
     {
-        SC::get().solve(*deg, *tol, *mode, *opt, *qr);
+        if (SCP::get().solver)
+            SCP::get().solve(*deg, *tol, *mode, *opt, *qr);
+        else
+            SC::get().solve(*deg, *tol, *mode, *opt, *qr);
+    }
+    void zchase_pseudo_(int* deg, double* tol, char* mode, char* opt, char* qr)
+    {
+        SZP::get().solve(*deg, *tol, *mode, *opt, *qr);
+    }
+    void cchase_pseudo_(int* deg, float* tol, char* mode, char* opt, char* qr)
+    {
+        SCP::get().solve(*deg, *tol, *mode, *opt, *qr);
     }
 
     void dchase_get_eigenpairs_(double* V, int* ld, double* ritzv)
@@ -393,19 +443,35 @@ extern "C"
     }
     void cchase_get_eigenpairs_(CHASE_B200_CF* V, int* ld, float* ritzv)
     {
-        if (ld)
+        if (ld && SCP::get().solver)
+            SCP::get().get_eigenpairs(reinterpret_cast<cf*>(V), *ld, ritzv);
+        else if (ld)
             SC::get().get_eigenpairs(reinterpret_cast<cf*>(V), *ld, ritzv);
     }
     void zchase_get_eigenpairs_(CHASE_B200_CD* V, int* ld, double* ritzv)
     {
-        if (ld)
+        if (ld && SZP::get().solver)
+            SZP::get().get_eigenpairs(reinterpret_cast<cd*>(V), *ld, ritzv);
+        else if (ld)
             SZ::get().get_eigenpairs(reinterpret_cast<cd*>(V), *ld, ritzv);
     }
 
     void dchase_get_resid_(double* r) { SD::get().get_resid(r); }
     void schase_get_resid_(float* r) { SS::get().get_resid(r); }
-    void cchase_get_resid_(float* r) { SC::get().get_resid(r); }
-    void zchase_get_resid_(double* r) { SZ::get().get_resid(r); }
+    void cchase_get_resid_(float* r)
+    {
+        if (SCP::get().solver)
+            SCP::get().get_resid(r);
+        else
+            SC::get().get_resid(r);
+    }
+    void zchase_get_resid_(double* r)
+    {
+        if (SZP::get().solver)
+            SZP::get().get_resid(r);
+        else
+            SZ::get().get_resid(r);
+    }
 
     void chase_set_tol_(double* tol)
     {

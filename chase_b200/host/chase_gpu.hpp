@@ -15,6 +15,13 @@
 //     include/chase_b200_kernels.h (no cuBLAS / cuSOLVER / cuRAND);
 //   * device panels are padded to a 16-element leading dimension (TMA/128-bit
 //     friendly) regardless of the caller's ldh/ldv.
+//
+// MatrixType = chase::matrix::PseudoHermitianMatrix<T, GPU> selects the
+// pseudo-Hermitian (BSE) problem class (reference: the same template argument,
+// chase_gpu.hpp:105-107): panels hold 2 (nev+nex) columns laid out as
+// [locked+ | active | K-conjugates of active | K-conjugates of locked+], the
+// filter runs on H^2 (HEMM_H2), QR orthogonalises against S [locked], RR is the
+// S-projected rayleighRitz_v2 and Lanczos uses the S H inner product.
 #pragma once
 #include "algorithm.hpp"
 #include "interface.hpp"
@@ -70,21 +77,27 @@ inline void fill_start_vectors(std::size_t N, std::size_t ncols, T* V, std::size
             V[i + j * ldv] = getRandomT<T>([&]() { return d(gen); });
 }
 
-template <class T>
+template <class T, class MatrixType = chase::matrix::Matrix<T, chase::platform::GPU>>
 class ChASEGPU : public ChaseBase<T>
 {
     using R = Base<T>;
     using KK = b200::K<T>;
     static constexpr bool kCplx = is_complex_t<T>::value;
+    static constexpr bool kPseudo =
+        std::is_same<MatrixType, chase::matrix::PseudoHermitianMatrix<T, chase::platform::GPU>>::value;
+    static_assert(!kPseudo || kCplx, "pseudo-Hermitian (BSE) problems are complex (reference: c/z only)");
 
 public:
     ChASEGPU(std::size_t N, std::size_t nev, std::size_t nex, T* H, std::size_t ldh, T* V1, std::size_t ldv,
              R* ritzv)
-        : N_(N), nev_(nev), nex_(nex), nevex_(nev + nex), H_(H), ldh_(ldh), V_(V1), ldv_(ldv), ritzv_(ritzv),
-          config_(N, nev, nex)
+        : N_(N), nev_(nev), nex_(nex), nevex_(nev + nex), nc_(kPseudo ? 2 * (nev + nex) : nev + nex), H_(H), ldh_(ldh),
+          V_(V1), ldv_(ldv), ritzv_(ritzv), config_(N, nev, nex)
     {
-        if (N == 0 || nevex_ == 0 || nevex_ > N)
-            throw std::invalid_argument("ChASEGPU: need 0 < nev+nex <= N");
+        if (N == 0 || nevex_ == 0 || nc_ > N)
+            throw std::invalid_argument(kPseudo ? "ChASEGPU: need 0 < 2 (nev+nex) <= N"
+                                                : "ChASEGPU: need 0 < nev+nex <= N");
+        if (kPseudo && N % 2 != 0)
+            throw std::invalid_argument("ChASEGPU: a pseudo-Hermitian matrix has even order");
         if (ldh < N || ldv < N)
             throw std::invalid_argument("ChASEGPU: leading dimension smaller than N");
         int ndev = 0;
@@ -92,26 +105,33 @@ public:
             throw std::runtime_error("ChASEGPU: no CUDA device available (this backend has no CPU fallback)");
         CB2_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         ld_ = roundup(N_, 16);
-        ldg_ = roundup(nevex_, 16);
+        ldg_ = roundup(nc_, 16);
         dH_ = alloc<T>(ld_ * N_);
-        dV1_ = alloc<T>(ld_ * nevex_);
-        dV2_ = alloc<T>(ld_ * nevex_);
-        dW_ = alloc<T>(ld_ * nevex_);
-        dG_ = alloc<T>(ldg_ * nevex_);
-        dZ_ = alloc<T>(ldg_ * nevex_);
-        heev_ws_bytes_ = chase_b200_heev_ws_bytes((int64_t)nevex_, kCplx ? 1 : 0);
+        dV1_ = alloc<T>(ld_ * nc_);
+        dV2_ = alloc<T>(ld_ * nc_);
+        dW_ = alloc<T>(ld_ * nc_);
+        dG_ = alloc<T>(ldg_ * nc_);
+        dZ_ = alloc<T>(ldg_ * nc_);
+        if (kPseudo)
+        {
+            // rayleighRitz_v2 works on three more small matrices (M, R^-1, products)
+            dM_ = alloc<T>(ldg_ * nc_);
+            dRinv_ = alloc<T>(ldg_ * nc_);
+            dT_ = alloc<T>(ldg_ * nc_);
+        }
+        heev_ws_bytes_ = chase_b200_heev_ws_bytes((int64_t)nc_, kCplx ? 1 : 0);
         heev_ws_ = alloc<unsigned char>(heev_ws_bytes_);
-        trsm_ws_bytes_ = chase_b200_trsm_ws_bytes((int64_t)nevex_, (int)sizeof(T));
+        trsm_ws_bytes_ = chase_b200_trsm_ws_bytes((int64_t)nc_, (int)sizeof(T));
         trsm_ws_ = alloc<unsigned char>(trsm_ws_bytes_);
-        splitk_ws_bytes_ = std::max<std::size_t>(std::size_t(64) << 20, 4 * nevex_ * nevex_ * 16);
+        splitk_ws_bytes_ = std::max<std::size_t>(std::size_t(64) << 20, 4 * nc_ * nc_ * 16);
         splitk_ws_ = alloc<unsigned char>(splitk_ws_bytes_);
-        dTheta_ = alloc<double>(nevex_);
-        dNorms_ = alloc<double>(nevex_);
+        dTheta_ = alloc<double>(nc_);
+        dNorms_ = alloc<double>(nc_);
         dInfo_ = alloc<int>(4);
-        dIdx_ = alloc<int>(2 * nevex_);
-        resid_.assign(nevex_, R(0));
-        perm_.resize(nevex_);
-        for (std::size_t i = 0; i < nevex_; ++i)
+        dIdx_ = alloc<int>(2 * nc_);
+        resid_.assign(nc_, R(0));
+        perm_.resize(nc_);
+        for (std::size_t i = 0; i < nc_; ++i)
             perm_[i] = (int)i;
         const char* e = std::getenv("CHASE_B200_DEVICE_RNG");
         device_rng_ = e && std::atoi(e) != 0;
@@ -132,28 +152,35 @@ public:
     {
         if (random && device_rng_)
         {
-            CB2_KCHECK(KK::rng_normal((int64_t)N_, (int64_t)nevex_, dV1_, (int64_t)ld_, 24141ull, stream_));
+            CB2_KCHECK(KK::rng_normal((int64_t)N_, (int64_t)nc_, dV1_, (int64_t)ld_, 24141ull, stream_));
         }
         else if (random && dV0_ != nullptr)
         {
-            // the reference stream is a pure function of (N, nev+nex, T): generated once, then kept on the device
-            CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nevex_, dV0_, (int64_t)ld_, dV1_, (int64_t)ld_, stream_));
+            // the reference stream is a pure function of (N, #columns, T): generated once, then kept on the device
+            CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nc_, dV0_, (int64_t)ld_, dV1_, (int64_t)ld_, stream_));
         }
         else
         {
             if (random)
             {
-                fill_start_vectors<T>(N_, nevex_, V_, ldv_);
+                fill_start_vectors<T>(N_, nc_, V_, ldv_);
             }
-            CB2_CHECK(cudaMemcpy2DAsync(dV1_, ld_ * sizeof(T), V_, ldv_ * sizeof(T), N_ * sizeof(T), nevex_,
+            CB2_CHECK(cudaMemcpy2DAsync(dV1_, ld_ * sizeof(T), V_, ldv_ * sizeof(T), N_ * sizeof(T), nc_,
                                         cudaMemcpyHostToDevice, stream_));
             if (random)
             {
-                dV0_ = alloc<T>(ld_ * nevex_);
-                CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nevex_, dV1_, (int64_t)ld_, dV0_, (int64_t)ld_, stream_));
+                dV0_ = alloc<T>(ld_ * nc_);
+                CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nc_, dV1_, (int64_t)ld_, dV0_, (int64_t)ld_, stream_));
             }
         }
-        CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nevex_, dV1_, (int64_t)ld_, dV2_, (int64_t)ld_, stream_));
+        if (random && kPseudo)
+        {
+            // damp the lower (de-excitation) block of the start vectors: T(0.001), chase_gpu.hpp:518-529
+            const std::size_t half = N_ / 2;
+            CB2_KCHECK(KK::scale_rows((int64_t)(N_ - half), (int64_t)nc_, dV1_ + half, (int64_t)ld_,
+                                      (double)(R)0.001, stream_));
+        }
+        CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nc_, dV1_, (int64_t)ld_, dV2_, (int64_t)ld_, stream_));
         // the host matrix is (re-)read at every solve: callers fill or perturb H
         // after construction (examples/4_interface/4_c_serial_chase.c:49-66).
         // keep_device_matrix(true) is the opt-out for callers whose H is unchanged
@@ -187,21 +214,97 @@ public:
         std::swap(dV1_, dV2_);
     }
 
-    void HEMM_H2(std::size_t, T, T, T, std::size_t, std::size_t = 0) override
+    // One filter step in H^2:  V2[cols] <- alpha H (H V1[cols]) + beta V2[cols] + gamma V1[cols]; swap.
+    // With gamma = -alpha c (the only form filter_H2 uses, c >= 0) the polynomial factorises,
+    //   alpha (H^2 - c I) = alpha (H - sqrt(c) I)(H + sqrt(c) I),
+    // so both products run through the filter HEMM with the shift folded into its epilogue and the gamma V1 pass of
+    // the reference (batchedAxpyScalar, chase_gpu.hpp:708-713) disappears.  Any other gamma takes the literal route.
+    // Columns: [locked_ + offset_left, locked_ + block - offset_right).  The reference always multiplies
+    // block - offset_right columns starting at offset_left, i.e. offset_left columns beyond the active half; those
+    // are K-conjugate slots that ApplyKconjugate rewrites right after the filter, so they are skipped here.
+    void HEMM_H2(std::size_t block, T alpha, T beta, T gamma, std::size_t offset_left,
+                 std::size_t offset_right = 0) override
     {
-        throw std::runtime_error("chase_b200: pseudo-Hermitian HEMM_H2 is not implemented yet");
+        if (!kPseudo)
+            throw std::runtime_error("chase_b200: HEMM_H2 needs MatrixType = PseudoHermitianMatrix");
+        flush_perm();
+        std::size_t ncols = (offset_right < block) ? block - offset_right : 0;
+        ncols = (offset_left < ncols) ? ncols - offset_left : 0;
+        if (ncols > 0)
+        {
+            const std::size_t c0 = offset_left + locked_;
+            T* in = dV1_ + c0 * ld_;
+            T* out = dV2_ + c0 * ld_;
+            T* tmp = dW_ + c0 * ld_;
+            const double a = b200::re_of(alpha), g = b200::re_of(gamma);
+            const double c = (a != 0.0) ? -g / a : -1.0;
+            const bool factorised = b200::im_of(alpha) == 0.0 && b200::im_of(gamma) == 0.0 && c >= 0.0 &&
+                                    !std::getenv("CHASE_B200_H2_AXPY");
+            if (factorised)
+            {
+                const double rc = std::sqrt(c);
+                CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)ncols, 1.0, 0.0, dH_, (int64_t)ld_, in, (int64_t)ld_, 0.0, 0.0,
+                                    tmp, (int64_t)ld_, -rc, nullptr, stream_));
+                CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)ncols, a, 0.0, dH_, (int64_t)ld_, tmp, (int64_t)ld_,
+                                    b200::re_of(beta), b200::im_of(beta), out, (int64_t)ld_, rc, nullptr, stream_));
+            }
+            else
+            {
+                CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)ncols, 1.0, 0.0, dH_, (int64_t)ld_, in, (int64_t)ld_, 0.0, 0.0,
+                                    tmp, (int64_t)ld_, 0.0, nullptr, stream_));
+                CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)ncols, a, b200::im_of(alpha), dH_, (int64_t)ld_, tmp,
+                                    (int64_t)ld_, b200::re_of(beta), b200::im_of(beta), out, (int64_t)ld_, 0.0, nullptr,
+                                    stream_));
+                if (ones_ == nullptr)
+                {
+                    ones_ = alloc<double>(nc_);
+                    std::vector<double> one(nc_, 1.0);
+                    CB2_CHECK(cudaMemcpy(ones_, one.data(), nc_ * sizeof(double), cudaMemcpyHostToDevice));
+                }
+                CB2_KCHECK(KK::axpy_cols((int64_t)N_, (int64_t)ncols, ones_, g, b200::im_of(gamma), in, (int64_t)ld_, out,
+                                         (int64_t)ld_, stream_));
+            }
+            hemm_cols_ += 2 * ncols;
+        }
+        std::swap(dV1_, dV2_);
     }
-    void ApplyKconjugate(std::size_t) override
+
+    // V1[:, 2 nevex - locked - block ...) <- K-conjugates of V1[:, locked ... locked + block)
+    void ApplyKconjugate(std::size_t block) override
     {
-        throw std::runtime_error("chase_b200: pseudo-Hermitian ApplyKconjugate is not implemented yet");
+        if (!kPseudo)
+            return; // reference: no-op for Hermitian problems (chase_gpu.hpp:721-723)
+        flush_perm();
+        if (block == 0)
+            return;
+        const std::size_t col_second = nc_ - locked_ - block;
+        CB2_KCHECK(KK::kconj((int64_t)N_, (int64_t)block, dV1_ + locked_ * ld_, (int64_t)ld_, dV1_ + col_second * ld_,
+                             (int64_t)ld_, stream_));
     }
 
     void QR(std::size_t /*fixednev*/, R cond) override
     {
         flush_perm();
         resid_ready_ = false;
-        // keep the locked vectors: CholQR runs on all nev+nex columns
+        // keep the locked vectors: CholQR runs on all columns
         CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)locked_, dV1_, (int64_t)ld_, dV2_, (int64_t)ld_, stream_));
+        if (kPseudo)
+        {
+            // layout [L+ | active | L-]: park L- in V2 too, then orthogonalise [S L+ | S L- | active]: the right
+            // eigenvectors are S-orthogonal, not orthogonal (chase_gpu.hpp:752-782)
+            const std::size_t act = nc_ - 2 * locked_;
+            CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)locked_, dV1_ + (nc_ - locked_) * ld_, (int64_t)ld_,
+                                 dV2_ + (nc_ - locked_) * ld_, (int64_t)ld_, stream_));
+            CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)locked_, dV1_, (int64_t)ld_, dW_, (int64_t)ld_, stream_));
+            CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)locked_, dV1_ + (nc_ - locked_) * ld_, (int64_t)ld_,
+                                 dW_ + locked_ * ld_, (int64_t)ld_, stream_));
+            CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)act, dV1_ + locked_ * ld_, (int64_t)ld_,
+                                 dW_ + 2 * locked_ * ld_, (int64_t)ld_, stream_));
+            std::swap(dV1_, dW_);
+            const std::size_t half = N_ / 2;
+            CB2_KCHECK(KK::scale_rows((int64_t)(N_ - half), (int64_t)(2 * locked_), dV1_ + half, (int64_t)ld_, -1.0,
+                                      stream_));
+        }
 
         int disable = config_.DoCholQR() ? 0 : 1;
         if (const char* s = std::getenv("CHASE_DISABLE_CHOLQR"))
@@ -249,6 +352,20 @@ public:
                                          ") and no Householder fallback is available yet");
         }
         qr_log_.push_back(last_qr_);
+        if (kPseudo)
+        {
+            // back to [L+ | active | L-] with the untouched locked columns
+            const std::size_t act = nc_ - 2 * locked_;
+            CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)act, dV1_ + 2 * locked_ * ld_, (int64_t)ld_,
+                                 dW_ + locked_ * ld_, (int64_t)ld_, stream_));
+            std::swap(dV1_, dW_);
+            CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)locked_, dV2_ + (nc_ - locked_) * ld_, (int64_t)ld_,
+                                 dV1_ + (nc_ - locked_) * ld_, (int64_t)ld_, stream_));
+            // with nothing locked the reference leaves the orthonormal block in BOTH panels (chase_gpu.hpp:922-938);
+            // LanczosDos copies columns of the second panel back, so the DoS start vectors depend on it
+            if (locked_ == 0)
+                CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)nc_, dV1_, (int64_t)ld_, dV2_, (int64_t)ld_, stream_));
+        }
         CB2_KCHECK(KK::lacpy((int64_t)N_, (int64_t)locked_, dV2_, (int64_t)ld_, dV1_, (int64_t)ld_, stream_));
     }
 
@@ -258,6 +375,11 @@ public:
         resid_ready_ = false;
         if (block == 0)
             return;
+        if (kPseudo)
+        {
+            rr_pseudo(ritzv, block);
+            return;
+        }
         T* Q = dV1_ + locked_ * ld_;
         T* W = dV2_ + locked_ * ld_;
         // W = A Q   (the reference forms A^H Q; A is Hermitian)
@@ -304,7 +426,7 @@ public:
             return;
         std::vector<double> th(k);
         T* W = dV2_ + locked_ * ld_;
-        if (resid_ready_ && resid_block_ == k && !std::getenv("CHASE_B200_RESID_HEMM"))
+        if (!kPseudo && resid_ready_ && resid_block_ == k && !std::getenv("CHASE_B200_RESID_HEMM"))
         {
             W = dW_ + locked_ * ld_; // prepared by RR
         }
@@ -332,14 +454,20 @@ public:
         lanczosIter_ = M;
         numLanczos_ = 1;
         std::vector<R> theta(M), tau(M), rv(M * M);
-        run_lanczos(M, 1, upperb, theta.data(), tau.data(), rv.data(), false);
+        if (kPseudo)
+            run_lanczos_pseudo(M, 1, upperb, theta.data(), tau.data(), rv.data(), false);
+        else
+            run_lanczos(M, 1, upperb, theta.data(), tau.data(), rv.data(), false);
     }
 
     void Lanczos(std::size_t M, std::size_t numvec, R* upperb, R* ritzv, R* Tau, R* ritzV) override
     {
         lanczosIter_ = M;
         numLanczos_ = numvec;
-        run_lanczos(M, numvec, upperb, ritzv, Tau, ritzV, true);
+        if (kPseudo)
+            run_lanczos_pseudo(M, numvec, upperb, ritzv, Tau, ritzV, true);
+        else
+            run_lanczos(M, numvec, upperb, ritzv, Tau, ritzV, true);
     }
 
     void LanczosDos(std::size_t idx, std::size_t m, T* ritzVc) override
@@ -376,9 +504,28 @@ public:
         is_sym_ = (h == 0);
         return is_sym_;
     }
-    bool isSym() override { return true; }
-    bool checkPseudoHermicityEasy() override { return false; }
-    bool isPseudoHerm() override { return false; }
+    bool isSym() override { return !kPseudo; }
+    // S H Hermitian?  (reference: flip the lower half, checkSymmetryEasy, flip back; chase_gpu.hpp:474-487)
+    bool checkPseudoHermicityEasy() override
+    {
+        if (N_ % 2 != 0)
+            return false;
+        CB2_CHECK(cudaMemcpy2DAsync(dH_, ld_ * sizeof(T), H_, ldh_ * sizeof(T), N_ * sizeof(T), N_,
+                                    cudaMemcpyHostToDevice, stream_));
+        const std::size_t half = N_ / 2;
+        CB2_KCHECK(KK::scale_rows((int64_t)half, (int64_t)N_, dH_ + half, (int64_t)ld_, -1.0, stream_));
+        unsigned long long* bad = reinterpret_cast<unsigned long long*>(dNorms_);
+        CB2_CHECK(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), stream_));
+        const double tol = (sizeof(R) == 8) ? 1e-10 : 1e-5;
+        CB2_KCHECK(KK::herm_check((int64_t)N_, dH_, (int64_t)ld_, tol, bad, stream_));
+        CB2_KCHECK(KK::scale_rows((int64_t)half, (int64_t)N_, dH_ + half, (int64_t)ld_, -1.0, stream_));
+        unsigned long long h = 0;
+        CB2_CHECK(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        matrix_on_device_ = true;
+        return h == 0;
+    }
+    bool isPseudoHerm() override { return kPseudo; }
     void symOrHermMatrix(char uplo) override
     {
         // acts on the caller's host matrix (re-uploaded at the next initVecs), like the reference
@@ -395,7 +542,7 @@ public:
     void End() override
     {
         flush_perm();
-        CB2_CHECK(cudaMemcpy2DAsync(V_, ldv_ * sizeof(T), dV1_, ld_ * sizeof(T), N_ * sizeof(T), nevex_,
+        CB2_CHECK(cudaMemcpy2DAsync(V_, ldv_ * sizeof(T), dV1_, ld_ * sizeof(T), N_ * sizeof(T), nc_,
                                     cudaMemcpyDeviceToHost, stream_));
         CB2_CHECK(cudaStreamSynchronize(stream_));
     }
@@ -405,7 +552,7 @@ public:
     std::size_t GetNex() override { return nex_; }
     std::size_t GetLanczosIter() override { return lanczosIter_; }
     std::size_t GetNumLanczos() override { return numLanczos_; }
-    std::size_t GetRitzvBlockSize() const override { return nevex_; }
+    std::size_t GetRitzvBlockSize() const override { return nc_; }
     R* GetRitzv() override { return ritzv_; }
     R* GetResid() override { return resid_.data(); }
     ChaseConfig<T>& GetConfig() override { return config_; }
@@ -457,7 +604,7 @@ private:
     }
     void reset_perm()
     {
-        for (std::size_t i = 0; i < nevex_; ++i)
+        for (std::size_t i = 0; i < nc_; ++i)
             perm_[i] = (int)i;
         perm_dirty_ = false;
     }
@@ -468,7 +615,7 @@ private:
             return;
         std::vector<int> idx;
         std::vector<int> src, dst;
-        for (std::size_t j = 0; j < nevex_; ++j)
+        for (std::size_t j = 0; j < nc_; ++j)
             if (perm_[j] != (int)j)
             {
                 src.push_back(perm_[j]);
@@ -494,7 +641,7 @@ private:
     // one CholQR round on all nev+nex columns; shift_boost > 0 adds the shifted-CholQR shift
     int chol_round(bool shifted, double shift_boost)
     {
-        const int64_t n = (int64_t)nevex_;
+        const int64_t n = (int64_t)nc_;
         CB2_KCHECK(KK::gemm(1, 0, n, n, (int64_t)N_, 1.0, 0.0, dV1_, (int64_t)ld_, dV1_, (int64_t)ld_, 0.0, 0.0, dG_,
                             (int64_t)ldg_, 1, splitk_ws_, splitk_ws_bytes_, stream_));
         if (shifted)
@@ -527,12 +674,124 @@ private:
         return chol_round(false, 0.0);
     }
 
-    void run_lanczos(std::size_t M, std::size_t numvec, R* upperb, R* Theta, R* Tau, R* ritzV, bool multi)
+    // Rayleigh-Ritz for the pseudo-Hermitian problem on Q = V1[:, locked_ ... locked_ + 2 block) (orthonormal):
+    // reference rayleighRitz_v2 (linalg/internal/cuda/rayleighRitz.hpp:510-784, CPU statement
+    // cpu/rayleighRitz.hpp:284-392).  A = Q^H S H Q = R^H R;  M = -R^-H (I - 2 Q2^H Q2) R^-1;  M z = w z (ascending);
+    // lambda = 1 / (-w): positive values first, ascending;  X = R^-1 Z[:, :block], columns normalised;
+    // V2[:, locked_ ... locked_ + block) = Q X;  swap.  The triangular solves of the reference become products with
+    // the explicit n x n inverse R^-1 (one TRSM on the identity), so everything large runs on the DMMA GEMM kernels.
+    void rr_pseudo(R* ritzv, std::size_t block)
+    {
+        const int64_t n = (int64_t)(2 * block), N = (int64_t)N_, half = (int64_t)(N_ / 2);
+        const int64_t ld = (int64_t)ld_, ldg = (int64_t)ldg_;
+        T* Q = dV1_ + locked_ * ld_;
+        T* W = dV2_ + locked_ * ld_;
+        CB2_KCHECK(KK::hemm(N, n, 1.0, 0.0, dH_, ld, Q, ld, 0.0, 0.0, W, ld, 0.0, nullptr, stream_));
+        CB2_KCHECK(KK::scale_rows(N - half, n, W + half, ld, -1.0, stream_));
+        CB2_KCHECK(KK::gemm(1, 0, n, n, N, 1.0, 0.0, Q, ld, W, ld, 0.0, 0.0, dG_, ldg, 0, splitk_ws_, splitk_ws_bytes_,
+                            stream_));
+        CB2_CHECK(cudaMemsetAsync(dInfo_, 0, sizeof(int), stream_));
+        CB2_KCHECK(KK::potrf(n, dG_, ldg, dInfo_, stream_));
+        int info = 0;
+        CB2_CHECK(cudaMemcpyAsync(&info, dInfo_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        if (info != 0)
+            throw std::runtime_error("chase_b200: Q^H S H Q is not positive definite in the pseudo-Hermitian RR "
+                                     "(potrf info=" + std::to_string(info) + "): S H must be positive definite");
+        // R^-1
+        CB2_CHECK(cudaMemsetAsync(dT_, 0, ldg_ * (std::size_t)n * sizeof(T), stream_));
+        CB2_KCHECK(KK::shift_diag(n, dT_, ldg, 1.0, stream_));
+        CB2_KCHECK(KK::trsm(n, n, dG_, ldg, dT_, ldg, dRinv_, ldg, trsm_ws_, trsm_ws_bytes_, stream_));
+        // M0 = I - 2 Q2^H Q2  (= Q^H S Q for orthonormal Q)
+        CB2_CHECK(cudaMemsetAsync(dM_, 0, ldg_ * (std::size_t)n * sizeof(T), stream_));
+        CB2_KCHECK(KK::shift_diag(n, dM_, ldg, 1.0, stream_));
+        CB2_KCHECK(KK::gemm(1, 0, n, n, N - half, -2.0, 0.0, Q + half, ld, Q + half, ld, 1.0, 0.0, dM_, ldg, 0,
+                            splitk_ws_, splitk_ws_bytes_, stream_));
+        // M = -R^-H M0 R^-1
+        CB2_KCHECK(KK::gemm(0, 0, n, n, n, 1.0, 0.0, dM_, ldg, dRinv_, ldg, 0.0, 0.0, dT_, ldg, 0, nullptr, 0, stream_));
+        CB2_KCHECK(KK::gemm(1, 0, n, n, n, -1.0, 0.0, dRinv_, ldg, dT_, ldg, 0.0, 0.0, dM_, ldg, 0, nullptr, 0,
+                            stream_));
+        std::vector<double> w((std::size_t)n);
+        int sweeps = 0;
+        const int rc = KK::heev(n, dM_, ldg, dZ_, ldg, w.data(), heev_ws_, heev_ws_bytes_, &sweeps, stream_);
+        if (rc != 0)
+            throw std::runtime_error("chase_b200: Hermitian eigensolver failed in the pseudo-Hermitian RR (rc=" +
+                                     std::to_string(rc) + ")");
+        heev_sweeps_ += sweeps;
+        for (int64_t i = 0; i < n; ++i)
+            ritzv[i] = R(1.0) / (R)(-w[(std::size_t)i]);
+        CB2_KCHECK(KK::gemm(0, 0, n, (int64_t)block, n, 1.0, 0.0, dRinv_, ldg, dZ_, ldg, 0.0, 0.0, dT_, ldg, 0, nullptr,
+                            0, stream_));
+        CB2_KCHECK(KK::normalize_cols(n, (int64_t)block, dT_, ldg, stream_));
+        CB2_KCHECK(KK::gemm(0, 0, N, (int64_t)block, n, 1.0, 0.0, Q, ld, dT_, ldg, 0.0, 0.0, W, ld, 0, nullptr, 0,
+                            stream_));
+        std::swap(dV1_, dV2_);
+    }
+
+    // Y <- H X for the (non-Hermitian) pseudo-Hermitian H through the HBM-bound A^H product: H = S H^H S
+    void pseudo_matvec(T* X, T* Y, int nv)
+    {
+        const int64_t N = (int64_t)N_, half = (int64_t)(N_ / 2), ld = (int64_t)ld_;
+        CB2_KCHECK(KK::scale_rows(N - half, nv, X + half, ld, -1.0, stream_));
+        CB2_KCHECK(KK::gemv_conjt(N, N, dH_, ld, X, ld, nv, Y, ld, stream_));
+        CB2_KCHECK(KK::scale_rows(N - half, nv, X + half, ld, -1.0, stream_));
+        CB2_KCHECK(KK::scale_rows(N - half, nv, Y + half, ld, -1.0, stream_));
+    }
+
+    // Lanczos in the S H inner product (reference cuda/lanczos.hpp:547-785, CPU statement cpu/lanczos.hpp:332-516):
+    // tridiagonal (d, e) per start vector, Ritz values / weights from the on-device tridiagonal eigensolver,
+    // *upperb = largest Ritz value of the first run.
+    void run_lanczos_pseudo(std::size_t M, std::size_t numvec, R* upperb, R* Theta, R* Tau, R* ritzV, bool multi)
     {
         flush_perm();
         if (M > 48)
             throw std::runtime_error("chase_b200: Lanczos with more than 48 steps is not supported yet");
         const int nv = (int)numvec, m = (int)M;
+        ensure_lanczos_buffers(M, numvec);
+        T* v0 = lan_v_;
+        T* v1 = lan_v_ + ld_ * numvec;
+        T* v2 = lan_v_ + 2 * ld_ * numvec;
+        const int64_t N = (int64_t)N_, ld = (int64_t)ld_;
+        CB2_CHECK(cudaMemsetAsync(lan_d_, 0, M * numvec * sizeof(double), stream_));
+        CB2_CHECK(cudaMemsetAsync(lan_e_, 0, M * numvec * sizeof(double), stream_));
+        CB2_KCHECK(KK::lacpy(N, nv, dV1_, ld, v1, ld, stream_));
+        pseudo_matvec(v1, v2, nv);
+        CB2_KCHECK(KK::lanczos_pseudo_norm(N, nv, -1, m, v1, v2, ld, lan_e_, lan_rb_, stream_));
+        for (int k = 0; k < m; ++k)
+        {
+            if (multi)
+                CB2_KCHECK(KK::lacpy(N, 1, v1 + (std::size_t)(nv - 1) * ld_, ld, dV1_ + (std::size_t)k * ld_, ld, stream_));
+            CB2_KCHECK(KK::lanczos_pseudo_step(N, nv, k, m, v0, v1, v2, ld, lan_d_, lan_rb_, stream_));
+            if (k == m - 1)
+                break;
+            T* t = v0;
+            v0 = v1;
+            v1 = v2;
+            v2 = t;
+            pseudo_matvec(v1, v2, nv);
+            CB2_KCHECK(KK::lanczos_pseudo_norm(N, nv, k, m, v1, v2, ld, lan_e_, lan_rb_, stream_));
+        }
+        if (multi)
+            CB2_KCHECK(KK::lacpy(N, nv, v1, ld, dV1_, ld, stream_));
+        CB2_KCHECK(chase_b200_tridiag_eig(m, nv, lan_d_, lan_e_, m, lan_w_, lan_Z_, stream_));
+        std::vector<double> w(M * numvec), Z(M * M * numvec);
+        CB2_CHECK(cudaMemcpyAsync(w.data(), lan_w_, w.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaMemcpyAsync(Z.data(), lan_Z_, Z.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        for (std::size_t i = 0; i < numvec; ++i)
+            for (std::size_t k = 0; k < M; ++k)
+            {
+                Theta[k + M * i] = (R)w[i * M + k];
+                const R z0 = (R)Z[i * M * M + 0 + k * M];
+                Tau[k + i * M] = std::abs(z0) * std::abs(z0);
+            }
+        for (std::size_t q = 0; q < M * M; ++q)
+            ritzV[q] = (R)Z[(numvec - 1) * M * M + q];
+        *upperb = Theta[M - 1];
+    }
+
+    void ensure_lanczos_buffers(std::size_t M, std::size_t numvec)
+    {
         if (lan_nv_ < numvec)
         {
             lan_v_ = alloc<T>(3 * ld_ * numvec);
@@ -547,6 +806,15 @@ private:
             lan_rb_ = alloc<double>(numvec + 1);
             lan_m_ = M * numvec;
         }
+    }
+
+    void run_lanczos(std::size_t M, std::size_t numvec, R* upperb, R* Theta, R* Tau, R* ritzV, bool multi)
+    {
+        flush_perm();
+        if (M > 48)
+            throw std::runtime_error("chase_b200: Lanczos with more than 48 steps is not supported yet");
+        const int nv = (int)numvec, m = (int)M;
+        ensure_lanczos_buffers(M, numvec);
         T* v0 = lan_v_;
         T* v1 = lan_v_ + ld_ * numvec;
         T* v2 = lan_v_ + 2 * ld_ * numvec;
@@ -599,6 +867,7 @@ private:
     }
 
     std::size_t N_, nev_, nex_, nevex_;
+    std::size_t nc_; // columns of the panels: nev+nex, or 2 (nev+nex) for pseudo-Hermitian problems
     T* H_;
     std::size_t ldh_;
     T* V_;
@@ -608,6 +877,8 @@ private:
     cudaStream_t stream_ = nullptr;
     std::size_t ld_ = 0, ldg_ = 0;
     T *dH_ = nullptr, *dV1_ = nullptr, *dV2_ = nullptr, *dW_ = nullptr, *dG_ = nullptr, *dZ_ = nullptr;
+    T *dM_ = nullptr, *dRinv_ = nullptr, *dT_ = nullptr; // pseudo-Hermitian RR only
+    double* ones_ = nullptr;
     T* dV0_ = nullptr; // device copy of the reference start block (parity mode), filled at the first random solve
     unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr;
     std::size_t heev_ws_bytes_ = 0, trsm_ws_bytes_ = 0, splitk_ws_bytes_ = 0;

@@ -146,10 +146,19 @@ public:
     }
     void HEMM_H2(std::size_t nev, T alpha, T beta, T gamma, std::size_t ol, std::size_t orr = 0) override
     {
+        if (trace_on_)
+            trace_.push_back("HEMM_H2 " + std::to_string(nev) + " " + fmt(std::real(alpha)) + " " + fmt(std::real(beta)) +
+                             " " + fmt(std::real(gamma)) + " " + std::to_string(ol) + " " + std::to_string(orr));
+        hemm_calls_++;
         chase_->HEMM_H2(nev, alpha, beta, gamma, ol, orr);
-        perf_.add_filtered_vecs(nev - orr);
+        perf_.add_filtered_vecs(2 * (nev - orr)); // reference performance.hpp:565-570
     }
-    void ApplyKconjugate(std::size_t block) override { chase_->ApplyKconjugate(block); }
+    void ApplyKconjugate(std::size_t block) override
+    {
+        if (trace_on_)
+            trace_.push_back("ApplyK " + std::to_string(block));
+        chase_->ApplyKconjugate(block);
+    }
     void FilterPhaseStart() override
     {
         perf_.start(ChasePerfData::Filter);

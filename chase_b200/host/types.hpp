@@ -59,6 +59,34 @@ inline T getRandomT(F&& f)
     }
 }
 
+// Matrix-type tags selecting the problem class of a backend, named like the reference's containers
+// (linalg/matrix/matrix.hpp:1202 Matrix<T, GPU>, :1597 PseudoHermitianMatrix<T, GPU>).  Here they carry no storage: the backends own
+// their device buffers and take the caller's raw host pointers.
+namespace platform
+{
+struct CPU
+{
+};
+struct GPU
+{
+};
+} // namespace platform
+namespace matrix
+{
+template <class T, class Platform = chase::platform::GPU>
+struct Matrix
+{
+    using value_type = T;
+    using platform_type = Platform;
+};
+template <class T, class Platform = chase::platform::GPU>
+struct PseudoHermitianMatrix
+{
+    using value_type = T;
+    using platform_type = Platform;
+};
+} // namespace matrix
+
 // type code used by the C-ABI kernel layer: 0 s, 1 d, 2 c, 3 z
 template <class T>
 constexpr int type_code()

@@ -190,3 +190,30 @@ def hemm_path(code, n, k, lda, ldb, ldc):
 
 def dmma_peak(iters=20000):
     return lib().chase_b200_dmma_peak(int(iters), _stream())
+
+
+# ---- pseudo-Hermitian (BSE) helpers ----------------------------------------------------------------------------
+def scale_rows(nrows, cols, X, ldx, a, row0=0):
+    """X[row0:row0+nrows, :cols] *= a."""
+    f = getattr(lib(), f"chase_b200_scale_rows_{_sfx(X)}")
+    p = ctypes.c_void_p(X.data_ptr() + row0 * X.element_size())
+    return _chk(f(ctypes.c_int64(nrows), ctypes.c_int64(cols), p, ctypes.c_int64(ldx), ctypes.c_double(a), _stream()),
+                "scale_rows")
+
+
+def kconj(rows, cols, src, lds, dst, ldd):
+    f = getattr(lib(), f"chase_b200_kconj_{_sfx(src)}")
+    return _chk(f(ctypes.c_int64(rows), ctypes.c_int64(cols), _ptr(src), ctypes.c_int64(lds), _ptr(dst),
+                  ctypes.c_int64(ldd), _stream()), "kconj")
+
+
+def lanczos_pseudo_norm(rows, nv, ke, M, v1, v2, ld, e, bnorm):
+    f = getattr(lib(), f"chase_b200_lanczos_pseudo_norm_{_sfx(v1)}")
+    return _chk(f(ctypes.c_int64(rows), int(nv), int(ke), int(M), _ptr(v1), _ptr(v2), ctypes.c_int64(ld), _ptr(e),
+                  _ptr(bnorm), _stream()), "lanczos_pseudo_norm")
+
+
+def lanczos_pseudo_step(rows, nv, k, M, v0, v1, v2, ld, d, bnorm):
+    f = getattr(lib(), f"chase_b200_lanczos_pseudo_step_{_sfx(v1)}")
+    return _chk(f(ctypes.c_int64(rows), int(nv), int(k), int(M), _ptr(v0), _ptr(v1), _ptr(v2), ctypes.c_int64(ld),
+                  _ptr(d), _ptr(bnorm), _stream()), "lanczos_pseudo_step")

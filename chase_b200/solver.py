@@ -7,6 +7,9 @@ reference (``/root/reference/interface/chase_c_interface.h:17-41``):
     s = ChASE(H, nev, nex)            # ?chase_init_   (H: column-major host matrix)
     r = s.solve(deg=20, tol=1e-10)    # ?chase_        ('R'/'A', 'S'/'N', 'C'/'H')
     s.finalize()                      # ?chase_finalize_
+
+Pseudo-Hermitian (BSE) problems use the ``?chase_init_pseudo_`` / ``?chase_pseudo_`` pair of the same interface
+(``chase_c_interface.h:42-58``): ``ChASE(H, nev, nex, pseudo=True)``; V then has ``2 (nev+nex)`` columns.
 """
 from __future__ import annotations
 
@@ -56,7 +59,7 @@ class ChASE:
 
     _active: dict = {}
 
-    def __init__(self, H: np.ndarray, nev: int, nex: int, V: np.ndarray | None = None):
+    def __init__(self, H: np.ndarray, nev: int, nex: int, V: np.ndarray | None = None, pseudo: bool = False):
         H = np.asarray(H)
         if H.ndim != 2 or H.shape[0] != H.shape[1]:
             raise ValueError("H must be square")
@@ -67,16 +70,20 @@ class ChASE:
         self.H = H
         self.N, self.nev, self.nex = H.shape[0], int(nev), int(nex)
         self.nevex = self.nev + self.nex
+        self.pseudo = bool(pseudo)
+        if self.pseudo and self.pfx not in ("c", "z"):
+            raise ValueError("pseudo-Hermitian problems are complex (cchase_init_pseudo_ / zchase_init_pseudo_)")
+        self.ncols = (2 if self.pseudo else 1) * self.nevex
         if V is None:
-            V = np.zeros((self.N, self.nevex), dtype=H.dtype, order="F")
+            V = np.zeros((self.N, self.ncols), dtype=H.dtype, order="F")
         else:
             V = np.asfortranarray(V, dtype=H.dtype)
-            assert V.shape == (self.N, self.nevex)
+            assert V.shape == (self.N, self.ncols)
         self.V = V
-        self.ritzv = np.zeros(self.nevex, dtype=self.rdt)
+        self.ritzv = np.zeros(self.ncols, dtype=self.rdt)
         self._lib = lib()
         flag = ctypes.c_int(0)
-        getattr(self._lib, f"{self.pfx}chase_init_")(
+        getattr(self._lib, f"{self.pfx}chase_init_pseudo_" if self.pseudo else f"{self.pfx}chase_init_")(
             _i(self.N), _i(self.nev), _i(self.nex), _p(self.H), _i(self.N), _p(self.V), _p(self.ritzv),
             ctypes.byref(flag),
         )
@@ -106,7 +113,7 @@ class ChASE:
             tol = 1e-10 if self.rdt == np.float64 else 1e-5
         L.chase_b200_trace_enable_(_i(1 if trace else 0))
         tolc = ctypes.c_double(tol) if self.rdt == np.float64 else ctypes.c_float(tol)
-        getattr(L, f"{self.pfx}chase_")(
+        getattr(L, f"{self.pfx}chase_pseudo_" if self.pseudo else f"{self.pfx}chase_")(
             _i(deg), ctypes.byref(tolc), ctypes.c_char_p(mode.encode()), ctypes.c_char_p(opt.encode()),
             ctypes.c_char_p(qr.encode()),
         )

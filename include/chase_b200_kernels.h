@@ -117,7 +117,24 @@ extern "C"
     /* A_ii += c (real part).  Replaces chase_shift_matrix (reference cuda/shiftDiagonal.cu:23-50). */                \
     int chase_b200_shift_diag_##X(int64_t n, void* A, int64_t lda, double c, void* stream);                           \
     /* Mirror one triangle onto the other (symOrHermMatrix, reference chase_gpu.hpp:472-505). */                      \
-    int chase_b200_herm_mirror_##X(int64_t n, void* A, int64_t lda, int from_upper, void* stream);
+    int chase_b200_herm_mirror_##X(int64_t n, void* A, int64_t lda, int from_upper, void* stream);                    \
+    /* X[0:nrows, 0:cols] *= a (X points at the first row to scale).  a = -1 on rows [N/2, N) is S X of the           \
+       pseudo-Hermitian path (reference cuda/flipSign.cu, chase_gpu.hpp:752-782); a = 1e-3 is the start-vector        \
+       damping of the lower block (chase_gpu.hpp:518-529). */                                                         \
+    int chase_b200_scale_rows_##X(int64_t nrows, int64_t cols, void* Xm, int64_t ldx, double a, void* stream);        \
+    /* K-conjugate partner vectors dst[:, j] = conj([src[rows/2:, j]; src[:rows/2, j]]), rows even, src/dst           \
+       disjoint.  Replaces the two lacpy + conjugate kernel of ChASEGPU::ApplyKconjugate (chase_gpu.hpp:718-742). */  \
+    int chase_b200_kconj_##X(int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst, int64_t ldd,        \
+                             void* stream);                                                                            \
+    /* S-inner-product Lanczos (pseudo-Hermitian H, v2 = H v1 on entry) for nv vectors, scalars on the device:        \
+       norm: beta = sqrt(Re <v1, S v2>), v1 /= beta, v2 /= beta, e[ke] = beta if ke >= 0, bnorm[v] = beta;            \
+       step: alpha = <v2, S v2>, v2 -= alpha v1, d[k] = alpha, and v2 -= beta v0 for 0 < k < M-1.                     \
+       Replace the dot/scal/axpy kernels of reference cuda/lanczos.hpp:547-785 (CPU: cpu/lanczos.hpp:332-516). */     \
+    int chase_b200_lanczos_pseudo_norm_##X(int64_t rows, int nv, int ke, int M, void* v1, void* v2, int64_t ld,       \
+                                           double* e_dev, double* bnorm_dev, void* stream);                           \
+    int chase_b200_lanczos_pseudo_step_##X(int64_t rows, int nv, int k, int M, const void* v0, const void* v1,        \
+                                           void* v2, int64_t ld, double* d_dev, const double* bnorm_dev,              \
+                                           void* stream);
 
     CHASE_B200_KERNEL_API(s)
     CHASE_B200_KERNEL_API(d)

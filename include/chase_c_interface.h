@@ -50,6 +50,20 @@ extern "C"
     void cchase_init_internal_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, int* init);
     void zchase_init_internal_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, int* init);
 
+    /* Sequential pseudo-Hermitian (BSE) problems, H = [[A, B], [-conj(B), -conj(A)]] with S H positive definite
+       (reference interface/chase_c_interface.h:42-58).  The caller allocates V with 2 (nev+nex) columns and ritzv
+       with 2 (nev+nex) entries; on return the first nev columns / entries hold the smallest positive eigenpairs.
+       Once a pseudo solver is initialised, ?chase_ / ?chase_get_eigenpairs_ / ?chase_finalize_ act on it, exactly as
+       in the reference (interface/chase_c_interface.cpp:2204-2231). */
+    void cchase_init_pseudo_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, CHASE_B200_CF* V, float* ritzv,
+                             int* init);
+    void cchase_init_pseudo_internal_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, int* init);
+    void zchase_init_pseudo_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, CHASE_B200_CD* V, double* ritzv,
+                             int* init);
+    void zchase_init_pseudo_internal_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, int* init);
+    void cchase_pseudo_(int* deg, float* tol, char* mode, char* opt, char* qr);
+    void zchase_pseudo_(int* deg, double* tol, char* mode, char* opt, char* qr);
+
     void dchase_finalize_(int* flag);
     void schase_finalize_(int* flag);
     void cchase_finalize_(int* flag);

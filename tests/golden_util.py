@@ -13,11 +13,16 @@ def load(name):
 
 def parse_trace(trace):
     """-> dict with hemm [(block, off_left)], qr [(locked, cond)], locks [n], ritzv [arrays], resid [arrays], lanczos"""
-    out = dict(hemm=[], qr=[], locks=[], ritzv=[], resid=[], shift=[], lanczos=None, dos=None, theta=None, tau=None)
+    out = dict(hemm=[], qr=[], locks=[], ritzv=[], resid=[], shift=[], lanczos=None, dos=None, theta=None, tau=None,
+               hemm_h2=[], applyk=[])
     for t in trace:
         f = t.split()
         if f[0] == "HEMM":
             out["hemm"].append((int(f[1]), int(f[4]), float(f[2]), float(f[3])))
+        elif f[0] == "HEMM_H2":  # (block, off_left, alpha, beta, gamma)
+            out["hemm_h2"].append((int(f[1]), int(f[5]), float(f[2]), float(f[3]), float(f[4])))
+        elif f[0] == "ApplyK":
+            out["applyk"].append(int(f[1]))
         elif f[0] == "QR":
             out["qr"].append((int(f[1]), float(f[2])))
         elif f[0] == "Lock":

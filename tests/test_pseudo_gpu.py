@@ -1,0 +1,218 @@
+"""GPU parity of the pseudo-Hermitian (BSE) path — SURVEY.md §8(f) rank 1, BASELINE.json configs[4].
+
+Through the reference-compatible C interface (?chase_init_pseudo_ / ?chase_pseudo_, host buffers) against
+* the golden traces of the UNMODIFIED reference CPU solver (oracle/_ref/chase_ref_cpu_p{z,c} = ChASECPU<T,
+  PseudoHermitianMatrix<T>> + Solve_pseudo; tests/golden/pseudo_*.json, tests/golden/make_golden.py),
+* the reference's own golden spectra (tests/golden/bse_fixtures/eigs_*.bin) and the analytically known spectrum of
+  the synthetic BSE matrix (oracle.chase_oracle.bse_matrix),
+and kernel by kernel through include/chase_b200_kernels.h against the numpy statements in oracle/chase_oracle.py.
+
+Parity bar (BASELINE.json north_star): identical iteration count, filtered-vector count, degree (HEMM_H2) schedule,
+lock counts; eigenvalues within 1e-10 relative in FP64 (1e-4 in FP32); residuals below the tolerance (early-locked
+pairs: < 1000 tol, algorithm.inc:752)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from oracle import chase_oracle as co  # noqa: E402  (checker only)
+from tests.golden_util import GOLDEN, load, parse_trace  # noqa: E402
+
+BSE = os.path.join(GOLDEN, "bse_fixtures")
+DT = {"pz": np.complex128, "pc": np.complex64, "z": np.complex128, "c": np.complex64}
+
+
+def K():
+    from chase_b200 import kernels
+
+    return kernels
+
+
+def _matrix(g):
+    dt = DT[g["type"]]
+    kind, arg = g["matrix"].split(":", 1)
+    if kind == "bse_fixture":
+        n = g["N"]
+        return np.asfortranarray(np.fromfile(os.path.join(BSE, arg), dtype=dt).reshape(n, n).T), None
+    if kind == "bse_synth":
+        return co.bse_matrix(g["N"], dt, seed=int(arg))
+    raise ValueError(g["matrix"])
+
+
+def _golden_spectrum(g):
+    kind, arg = g["matrix"].split(":", 1)
+    if kind == "bse_fixture":
+        e = np.fromfile(os.path.join(BSE, "eigs_" + arg), dtype=DT[g["type"]]).real.astype(np.float64)
+        return np.sort(e[e > 0])
+    return co.bse_matrix(g["N"], DT[g["type"]], seed=int(arg))[1]
+
+
+def _solve(H, g, **kw):
+    import chase_b200
+
+    with chase_b200.ChASE(H, g["nev"], g["nex"], pseudo=True) as s:
+        if "numlanczos" in g:
+            s.set(num_lanczos=g["numlanczos"], lanczos_iter=g["lanczositer"])
+        return s.solve(deg=g["deg"], tol=g["tol"], opt="S" if g["opt"] else "N", trace=True, **kw)
+
+
+# ---------------------------------------------------------------- kernels
+@pytest.mark.parametrize("t", ["z", "c"])
+def test_scale_rows_is_S_times_X(t):
+    k = K()
+    rng = np.random.default_rng(5)
+    N, m, ld = 130, 7, 144
+    X = (rng.standard_normal((N, m)) + 1j * rng.standard_normal((N, m))).astype(DT[t])
+    d = k.colmajor(X, ld)
+    k.scale_rows(N - N // 2, m, d, ld, -1.0, row0=N // 2)
+    torch.cuda.synchronize()
+    assert np.array_equal(k.to_numpy(d, N), co.flip_lower_half(X))
+    k.scale_rows(N - N // 2, 3, d, ld, 0.001, row0=N // 2)  # start-vector damping on 3 columns only
+    torch.cuda.synchronize()
+    out = k.to_numpy(d, N)
+    ref = co.flip_lower_half(X)
+    ref[N // 2:, :3] *= DT[t](0.001).real
+    assert np.allclose(out, ref, rtol=1e-6 if t == "c" else 1e-15, atol=0)
+    assert np.all(d.cpu().numpy()[:, N:] == 0)
+
+
+@pytest.mark.parametrize("t", ["z", "c"])
+def test_kconj_matches_oracle(t):
+    k = K()
+    rng = np.random.default_rng(6)
+    N, m, ld = 96, 5, 112
+    X = (rng.standard_normal((N, m)) + 1j * rng.standard_normal((N, m))).astype(DT[t])
+    src = k.colmajor(X, ld)
+    dst = k.colmajor(np.zeros_like(X), ld)
+    k.kconj(N, m, src, ld, dst, ld)
+    torch.cuda.synchronize()
+    assert np.array_equal(k.to_numpy(dst, N), co.k_conjugate(X))
+    with pytest.raises(RuntimeError):
+        k.kconj(N - 1, m, src, ld, dst, ld)  # odd order is not a pseudo-Hermitian layout
+
+
+def test_lanczos_pseudo_kernels_reproduce_the_tridiagonal():
+    """Device sequence of ChASEGPU::run_lanczos_pseudo (H x through the A^H product and S) vs cpu/lanczos.hpp:332-516."""
+    k = K()
+    N, M, nv = 200, 16, 4
+    H = np.asfortranarray(np.fromfile(os.path.join(BSE, "cdouble_random_BSE.bin"), dtype=np.complex128).reshape(N, N).T)
+    V = co.init_vectors(N, 2 * M, np.complex128)
+    Theta, Tau, rV, d_ref, e_ref = co.lanczos_pseudo(H, V.copy(), M, nv)
+    ld = 208
+    dH = k.colmajor(H, ld)
+    v0 = k.colmajor(np.zeros((N, nv), dtype=np.complex128), ld)
+    v1 = k.colmajor(V[:, :nv], ld)
+    v2 = k.colmajor(np.zeros((N, nv), dtype=np.complex128), ld)
+    d = torch.zeros(M * nv, dtype=torch.float64, device="cuda")
+    e = torch.zeros(M * nv, dtype=torch.float64, device="cuda")
+    bn = torch.zeros(nv + 1, dtype=torch.float64, device="cuda")
+    half = N // 2
+
+    def matvec(x, y):
+        k.scale_rows(N - half, nv, x, ld, -1.0, row0=half)
+        k.gemv_conjt(N, N, dH, ld, x, ld, nv, y, ld)
+        k.scale_rows(N - half, nv, x, ld, -1.0, row0=half)
+        k.scale_rows(N - half, nv, y, ld, -1.0, row0=half)
+
+    matvec(v1, v2)
+    torch.cuda.synchronize()
+    assert np.linalg.norm(k.to_numpy(v2, N) - H @ V[:, :nv]) < 1e-11 * np.linalg.norm(H)
+    k.lanczos_pseudo_norm(N, nv, -1, M, v1, v2, ld, e, bn)
+    for j in range(M):
+        k.lanczos_pseudo_step(N, nv, j, M, v0, v1, v2, ld, d, bn)
+        if j == M - 1:
+            break
+        v0, v1, v2 = v1, v2, v0
+        matvec(v1, v2)
+        k.lanczos_pseudo_norm(N, nv, j, M, v1, v2, ld, e, bn)
+    torch.cuda.synchronize()
+    dd = d.cpu().numpy().reshape(nv, M).T
+    ee = e.cpu().numpy().reshape(nv, M).T
+    assert np.max(np.abs(dd - d_ref)) < 1e-8 * np.abs(d_ref).max()
+    assert np.max(np.abs(ee - e_ref)) < 1e-8 * np.abs(e_ref).max()
+
+
+# ---------------------------------------------------------------- full solves
+def _check(g, res, eig_tol, strict=True):
+    p = g["problems"][0]
+    ref, got = parse_trace(p["trace"]), parse_trace(res.trace)
+    nev = g["nev"]
+    if strict:
+        assert res.iterations == p["iterations"]
+        assert res.filtered_vecs == p["filtered_vecs"]
+        assert [h[:2] for h in got["hemm_h2"]] == [h[:2] for h in ref["hemm_h2"]]  # identical degree schedule
+        for a, b in zip(got["hemm_h2"], ref["hemm_h2"]):
+            assert a[2:] == pytest.approx(b[2:], rel=1e-6)
+        assert got["locks"] == ref["locks"]
+        assert got["applyk"] == ref["applyk"]
+        assert got["dos"] == ref["dos"]
+        assert [q[0] for q in got["qr"]] == [q[0] for q in ref["qr"]]
+        for (_, c1), (_, c2) in zip(got["qr"], ref["qr"]):
+            assert c1 == pytest.approx(c2, rel=1e-4)
+        assert int(res.stats["swaps"]) == p["swaps"]
+    refv = np.array(p["ritzv"][:nev])
+    assert np.max(np.abs(res.ritzv[:nev] - refv) / np.abs(refv)) < eig_tol
+    exact = _golden_spectrum(g)[:nev]
+    assert np.max(np.abs(res.ritzv[:nev] - exact) / exact) < eig_tol
+    assert np.all(res.resid[:nev] < 1000 * g["tol"])
+    if strict:
+        assert np.sum(res.resid[:nev] > g["tol"]) == np.sum(np.array(p["resid"][:nev]) > g["tol"])
+
+
+@pytest.mark.parametrize("name", ["pseudo_bse_z_N200", "pseudo_bse_z_N200_dflt", "pseudo_synth_z_N600",
+                                  "pseudo_synth_z_N600_noopt"])
+def test_solve_pseudo_matches_reference_trace_fp64(name):
+    g = load(name)
+    H, _ = _matrix(g)
+    res = _solve(H, g)
+    _check(g, res, 1e-10)
+    nev, N = g["nev"], g["N"]
+    V = res.V[:, :nev]
+    # what the reference's pseudo-Hermitian tests assert: recomputed residuals of the returned pairs
+    r = np.linalg.norm(H @ V - V * res.ritzv[:nev], axis=0)
+    assert np.all(r < 1e-7 * np.abs(res.ritzv[:nev]).max())
+    # returned vectors have unit 2-norm (rayleighRitz_v2 normalisation) and positive S-norm
+    assert np.allclose(np.linalg.norm(V, axis=0), 1.0, atol=1e-10)
+    assert np.all(np.einsum("ij,ij->j", V.conj(), co.flip_lower_half(V)).real > 0)
+    # the K-conjugate partners of the locked pairs sit at the far end of the 2 (nev+nex) columns
+    ncols = 2 * (g["nev"] + g["nex"])
+    assert res.V.shape == (N, ncols)
+
+
+def test_solve_pseudo_fp32_within_tolerance():
+    g = load("pseudo_bse_c_N200")
+    H, _ = _matrix(g)
+    res = _solve(H, g)
+    _check(g, res, 1e-4, strict=False)
+
+
+def test_hemm_h2_factorised_equals_literal_form(monkeypatch):
+    """alpha (H - sqrt(c))(H + sqrt(c)) V + beta W (two shifted HEMMs) vs alpha H (H V) + beta W + gamma V (reference
+    form, chase_gpu.hpp:680-716): same solve, same decisions, eigenvalues to 1e-12."""
+    g = load("pseudo_bse_z_N200_dflt")
+    H, _ = _matrix(g)
+    a = _solve(H, g)
+    monkeypatch.setenv("CHASE_B200_H2_AXPY", "1")
+    b = _solve(H, g)
+    monkeypatch.delenv("CHASE_B200_H2_AXPY")
+    _check(g, b, 1e-10)
+    assert a.iterations == b.iterations and a.filtered_vecs == b.filtered_vecs
+    nev = g["nev"]
+    assert np.max(np.abs(a.ritzv[:nev] - b.ritzv[:nev]) / np.abs(b.ritzv[:nev])) < 1e-12
+
+
+def test_pseudo_and_hermitian_singletons_do_not_interfere():
+    """zchase_ dispatches to the pseudo solver only while one exists (chase_c_interface.cpp:2204-2231)."""
+    import chase_b200
+
+    g = load("pseudo_bse_z_N200_dflt")
+    H, _ = _matrix(g)
+    res = _solve(H, g)
+    assert res.iterations >= 1
+    Hc = co.clement(128, np.complex128)
+    with chase_b200.ChASE(Hc, 10, 6) as s:
+        r = s.solve(deg=16, tol=1e-10)
+    assert np.allclose(r.ritzv[:10], -128 + 2 * np.arange(10), atol=1e-8)
