@@ -278,6 +278,23 @@ __global__ void scale_rows_kernel(long long nrows, long long cols, T* X, long lo
             X[i + j * ldx] = narrow<T>(cmul(a, (C)widen(X[i + j * ldx])));
 }
 
+// distributed panels: X[i, j] *= a for the local rows whose GLOBAL index grow[i] >= g0 (S X on a row-split panel,
+// reference: flipSign on the local lower-half rows, linalg/distMatrix/distMultiVector.hpp:1879-2060 context)
+template <class T>
+__global__ void scale_rows_map_kernel(long long rows, long long cols, const long long* grow, long long g0, T* X,
+                                      long long ldx, double a)
+{
+    using C = typename Traits<T>::comp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+         i += (long long)gridDim.x * blockDim.x)
+    {
+        if (grow[i] < g0)
+            continue;
+        for (long long j = blockIdx.y; j < cols; j += gridDim.y)
+            X[i + j * ldx] = narrow<T>(cmul(a, (C)widen(X[i + j * ldx])));
+    }
+}
+
 // K-conjugate partner vectors: dst[:, j] = conj([src[half:2 half, j]; src[0:half, j]])  (src and dst: disjoint columns)
 template <class T>
 __global__ void kconj_kernel(long long half, long long cols, const T* src, long long lds, T* dst, long long ldd)

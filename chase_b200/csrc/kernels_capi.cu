@@ -682,6 +682,16 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
+    extern "C" int chase_b200_scale_rows_map_##X(int64_t rows, int64_t cols, const int64_t* grow, int64_t g0,         \
+                                                 void* Xm, int64_t ldx, double a, void* st)                           \
+    {                                                                                                                  \
+        if (rows <= 0 || cols <= 0)                                                                                    \
+            return 0;                                                                                                  \
+        scale_rows_map_kernel<TT><<<grid2d(rows, cols), 256, 0, kcount(S(st))>>>(rows, cols, (const long long*)grow,  \
+                                                                                 g0, (TT*)Xm, ldx, a);                 \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
     extern "C" int chase_b200_kconj_##X(int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst,          \
                                         int64_t ldd, void* st)                                                        \
     {                                                                                                                  \

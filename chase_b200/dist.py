@@ -110,9 +110,11 @@ class PChASE:
     """p?chase_init_[blockcyclic_] / p?chase_ / p?chase_finalize_ on this rank's local pieces (host numpy buffers)."""
 
     def __init__(self, world: World, N: int, nev: int, nex: int, H_loc: np.ndarray, grid=None, major="R", mb=0, nb=0,
-                 V_loc: np.ndarray | None = None):
+                 V_loc: np.ndarray | None = None, pseudo: bool = False):
         self.world = world
         self.N, self.nev, self.nex, self.nevex = int(N), int(nev), int(nex), int(nev + nex)
+        self.pseudo = bool(pseudo)  # p?chase_init_pseudo_[blockcyclic_]: 2 (nev+nex) columns
+        self.ncols = (2 if self.pseudo else 1) * self.nevex
         self.grid = grid or grid_dims(world.size)
         self.major = major
         self.mb, self.nb = int(mb), int(nb)
@@ -134,22 +136,25 @@ class PChASE:
         self.pfx = _PFX[self._dtype]
         self.rdt = _REAL[self.pfx]
         self.H = H_loc
+        if self.pseudo and self.pfx not in ("c", "z"):
+            raise ValueError("pseudo-Hermitian problems are complex")
         if V_loc is None:
-            V_loc = np.zeros((max(self.m, 1), self.nevex), dtype=self._dtype, order="F")
-        assert V_loc.flags.f_contiguous and V_loc.shape == (max(self.m, 1), self.nevex)
+            V_loc = np.zeros((max(self.m, 1), self.ncols), dtype=self._dtype, order="F")
+        assert V_loc.flags.f_contiguous and V_loc.shape == (max(self.m, 1), self.ncols)
         self.V = V_loc
-        self.ritzv = np.zeros(self.nevex, dtype=self.rdt)
+        self.ritzv = np.zeros(self.ncols, dtype=self.rdt)
         self._lib = lib()
         flag = ctypes.c_int(0)
         ldh = ctypes.byref(ctypes.c_int(max(self.m, 1)))
         gm = ctypes.c_char_p(major.encode())
         comm = ctypes.byref(world.handle)
+        ps = "pseudo_" if self.pseudo else ""
         if mb == 0 and nb == 0:
-            getattr(self._lib, f"p{self.pfx}chase_init_")(
+            getattr(self._lib, f"p{self.pfx}chase_init_{ps}")(
                 _i(N), _i(nev), _i(nex), _i(self.m), _i(self.n), self._hp(), ldh, _p(self.V), _p(self.ritzv),
                 _i(r), _i(c), gm, comm, ctypes.byref(flag))
         else:
-            getattr(self._lib, f"p{self.pfx}chase_init_blockcyclic_")(
+            getattr(self._lib, f"p{self.pfx}chase_init_{ps}blockcyclic_")(
                 _i(N), _i(nev), _i(nex), _i(mb), _i(nb), self._hp(), ldh, _p(self.V), _p(self.ritzv), _i(r), _i(c),
                 gm, _i(0), _i(0), comm, ctypes.byref(flag))
         if flag.value != 1:

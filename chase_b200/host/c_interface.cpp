@@ -183,11 +183,13 @@ struct Seq
 };
 
 // Distributed solver singleton per scalar type (reference ChASE_DIST, chase_c_interface.cpp:535-640).
-template <class T>
+template <class T, class MT = chase::matrix::Matrix<T, chase::platform::GPU>>
 struct Dist
 {
     using R = chase::Base<T>;
-    std::unique_ptr<chase::Impl::pChASEGPU<T>> solver;
+    static constexpr std::size_t kWidth =
+        std::is_same<MT, chase::matrix::PseudoHermitianMatrix<T, chase::platform::GPU>>::value ? 2 : 1;
+    std::unique_ptr<chase::Impl::pChASEGPU<T, MT>> solver;
     std::vector<T> vec;
     std::vector<R> ritz;
     T* V = nullptr;
@@ -216,16 +218,16 @@ struct Dist
             V = V_;
             if (V == nullptr)
             {
-                vec.assign(std::max<std::size_t>(m_loc, 1) * (std::size_t)(nev + nex), T(0));
+                vec.assign(std::max<std::size_t>(m_loc, 1) * kWidth * (std::size_t)(nev + nex), T(0));
                 V = vec.data();
             }
             ritzv = ritzv_;
             if (ritzv == nullptr)
             {
-                ritz.assign((std::size_t)(nev + nex), R(0));
+                ritz.assign(kWidth * (std::size_t)(nev + nex), R(0));
                 ritzv = ritz.data();
             }
-            solver.reset(new chase::Impl::pChASEGPU<T>((std::size_t)N_, (std::size_t)nev, (std::size_t)nex, *w, dim0,
+            solver.reset(new chase::Impl::pChASEGPU<T, MT>((std::size_t)N_, (std::size_t)nev, (std::size_t)nex, *w, dim0,
                                                        dim1, grid_major, (std::size_t)mb, (std::size_t)nb, H,
                                                        (std::size_t)ldh, V, std::max<std::size_t>(m_loc, 1), ritzv));
         }
@@ -277,6 +279,8 @@ using PD = Dist<double>;
 using PS = Dist<float>;
 using PZ = Dist<std::complex<double>>;
 using PC = Dist<std::complex<float>>;
+using PZP = Dist<std::complex<double>, chase::matrix::PseudoHermitianMatrix<std::complex<double>, chase::platform::GPU>>;
+using PCP = Dist<std::complex<float>, chase::matrix::PseudoHermitianMatrix<std::complex<float>, chase::platform::GPU>>;
 
 template <class F>
 void with_active_config(F&& f)
@@ -301,6 +305,10 @@ void with_active_config(F&& f)
         f(PZ::get().solver->GetConfig());
     else if (PC::get().solver)
         f(PC::get().solver->GetConfig());
+    else if (PZP::get().solver)
+        f(PZP::get().solver->GetConfig());
+    else if (PCP::get().solver)
+        f(PCP::get().solver->GetConfig());
 }
 
 size_t copy_out(const std::string& s, char* buf, size_t cap)
@@ -550,8 +558,8 @@ extern "C"
     }
 
     // ---- distributed entry points (reference chase_c_interface.h:61-195) ---------------------------------
-#define CB2_DIST_API(X, TT, CT, RT, SINGLETON)                                                                         \
-    void p##X##chase_init_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, CT* V, RT* ritzv, int* dim0,  \
+#define CB2_DIST_INIT_API(X, PSEUDO, TT, CT, RT, SINGLETON)                                                            \
+    void p##X##chase_init_##PSEUDO(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, CT* V, RT* ritzv, int* dim0,  \
                            int* dim1, char* grid_major, MPI_Comm* comm, int* init)                                     \
     {                                                                                                                  \
         (void)m;                                                                                                       \
@@ -559,7 +567,7 @@ extern "C"
         *init = SINGLETON::get().init(*N, *nev, *nex, 0, 0, reinterpret_cast<TT*>(H), *ldh, reinterpret_cast<TT*>(V), \
                                       ritzv, *dim0, *dim1, *grid_major, comm ? *comm : nullptr);                       \
     }                                                                                                                  \
-    void p##X##chase_init_internal_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, int* dim0, int* dim1,\
+    void p##X##chase_init_##PSEUDO##internal_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, int* dim0, int* dim1,\
                                     char* grid_major, MPI_Comm* comm, int* init)                                       \
     {                                                                                                                  \
         (void)m;                                                                                                       \
@@ -567,7 +575,7 @@ extern "C"
         *init = SINGLETON::get().init(*N, *nev, *nex, 0, 0, reinterpret_cast<TT*>(H), *ldh, nullptr, nullptr, *dim0,  \
                                       *dim1, *grid_major, comm ? *comm : nullptr);                                     \
     }                                                                                                                  \
-    void p##X##chase_init_blockcyclic_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H, int* ldh, CT* V,  \
+    void p##X##chase_init_##PSEUDO##blockcyclic_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H, int* ldh, CT* V,  \
                                        RT* ritzv, int* dim0, int* dim1, char* grid_major, int* irsrc, int* icsrc,      \
                                        MPI_Comm* comm, int* init)                                                      \
     {                                                                                                                  \
@@ -581,7 +589,7 @@ extern "C"
                                       reinterpret_cast<TT*>(V), ritzv, *dim0, *dim1, *grid_major,                      \
                                       comm ? *comm : nullptr);                                                         \
     }                                                                                                                  \
-    void p##X##chase_init_blockcyclic_internal_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H, int* ldh, \
+    void p##X##chase_init_##PSEUDO##blockcyclic_internal_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H, int* ldh, \
                                                 int* dim0, int* dim1, char* grid_major, int* irsrc, int* icsrc,        \
                                                 MPI_Comm* comm, int* init)                                             \
     {                                                                                                                  \
@@ -589,7 +597,8 @@ extern "C"
         (void)icsrc;                                                                                                   \
         *init = SINGLETON::get().init(*N, *nev, *nex, *mbsize, *nbsize, reinterpret_cast<TT*>(H), *ldh, nullptr,      \
                                       nullptr, *dim0, *dim1, *grid_major, comm ? *comm : nullptr);                     \
-    }                                                                                                                  \
+    }
+#define CB2_DIST_RUN_API(X, TT, CT, RT, SINGLETON)                                                                     \
     void p##X##chase_(int* deg, RT* tol, char* mode, char* opt, char* qr)                                              \
     {                                                                                                                  \
         SINGLETON::get().solve(*deg, *tol, *mode, *opt, *qr);                                                          \
@@ -605,12 +614,50 @@ extern "C"
             SINGLETON::get().get_eigenpairs(reinterpret_cast<TT*>(V), *ld, ritzv);                                     \
     }                                                                                                                  \
     void p##X##chase_get_resid_(RT* r) { SINGLETON::get().get_resid(r); }
+    // complex types: the pseudo-Hermitian singleton takes the call while it exists (reference
+    // chase_c_interface.cpp:1976-1996, 2017-2037)
+#define CB2_DIST_RUN_API_CPLX(X, TT, CT, RT, SINGLETON, PSINGLETON)                                                    \
+    void p##X##chase_(int* deg, RT* tol, char* mode, char* opt, char* qr)                                              \
+    {                                                                                                                  \
+        if (PSINGLETON::get().solver)                                                                                  \
+            PSINGLETON::get().solve(*deg, *tol, *mode, *opt, *qr);                                                     \
+        else                                                                                                           \
+            SINGLETON::get().solve(*deg, *tol, *mode, *opt, *qr);                                                      \
+    }                                                                                                                  \
+    void p##X##chase_finalize_(int* flag)                                                                              \
+    {                                                                                                                  \
+        SINGLETON::get().finalize();                                                                                   \
+        PSINGLETON::get().finalize();                                                                                  \
+        *flag = 0;                                                                                                     \
+    }                                                                                                                  \
+    void p##X##chase_get_eigenpairs_(CT* V, int* ld, RT* ritzv)                                                        \
+    {                                                                                                                  \
+        if (ld && PSINGLETON::get().solver)                                                                            \
+            PSINGLETON::get().get_eigenpairs(reinterpret_cast<TT*>(V), *ld, ritzv);                                    \
+        else if (ld)                                                                                                   \
+            SINGLETON::get().get_eigenpairs(reinterpret_cast<TT*>(V), *ld, ritzv);                                     \
+    }                                                                                                                  \
+    void p##X##chase_get_resid_(RT* r)                                                                                 \
+    {                                                                                                                  \
+        if (PSINGLETON::get().solver)                                                                                  \
+            PSINGLETON::get().get_resid(r);                                                                            \
+        else                                                                                                           \
+            SINGLETON::get().get_resid(r);                                                                             \
+    }
 
-    CB2_DIST_API(d, double, double, double, PD)
-    CB2_DIST_API(s, float, float, float, PS)
-    CB2_DIST_API(z, cd, CHASE_B200_CD, double, PZ)
-    CB2_DIST_API(c, cf, CHASE_B200_CF, float, PC)
-#undef CB2_DIST_API
+    CB2_DIST_INIT_API(d, , double, double, double, PD)
+    CB2_DIST_INIT_API(s, , float, float, float, PS)
+    CB2_DIST_INIT_API(z, , cd, CHASE_B200_CD, double, PZ)
+    CB2_DIST_INIT_API(c, , cf, CHASE_B200_CF, float, PC)
+    CB2_DIST_INIT_API(z, pseudo_, cd, CHASE_B200_CD, double, PZP)
+    CB2_DIST_INIT_API(c, pseudo_, cf, CHASE_B200_CF, float, PCP)
+    CB2_DIST_RUN_API(d, double, double, double, PD)
+    CB2_DIST_RUN_API(s, float, float, float, PS)
+    CB2_DIST_RUN_API_CPLX(z, cd, CHASE_B200_CD, double, PZ, PZP)
+    CB2_DIST_RUN_API_CPLX(c, cf, CHASE_B200_CF, float, PC, PCP)
+#undef CB2_DIST_INIT_API
+#undef CB2_DIST_RUN_API
+#undef CB2_DIST_RUN_API_CPLX
 
     // Device-resident input for matrices that should never exist on the host (C4: 28.8 GB per GPU): copies a
     // column-major device block (m_loc x n_loc, leading dimension ld_src) into the active distributed solver and marks
@@ -642,8 +689,8 @@ extern "C"
         {
             case 'd': return load(PD::get());
             case 's': return load(PS::get());
-            case 'z': return load(PZ::get());
-            case 'c': return load(PC::get());
+            case 'z': return PZP::get().solver ? load(PZP::get()) : load(PZ::get());
+            case 'c': return PCP::get().solver ? load(PCP::get()) : load(PC::get());
         }
         return -1;
     }

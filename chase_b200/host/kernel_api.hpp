@@ -40,6 +40,7 @@ struct K;
         static constexpr auto shift_diag = chase_b200_shift_diag_##X;                                                  \
         static constexpr auto herm_mirror = chase_b200_herm_mirror_##X;                                                \
         static constexpr auto scale_rows = chase_b200_scale_rows_##X;                                                  \
+        static constexpr auto scale_rows_map = chase_b200_scale_rows_map_##X;                                          \
         static constexpr auto kconj = chase_b200_kconj_##X;                                                            \
         static constexpr auto lanczos_pseudo_norm = chase_b200_lanczos_pseudo_norm_##X;                                \
         static constexpr auto lanczos_pseudo_step = chase_b200_lanczos_pseudo_step_##X;                                \

@@ -19,6 +19,13 @@
 // redistribution per iteration); Lanczos keeps its numvec vectors replicated in full length, so its vector updates
 // need no scalar allreduces (3 per step in nccl/lanczos.hpp:256-322); Gram / projected matrices are broadcast from
 // one replica so that all ranks take bit-identical decisions; Swap storms become one gather pass.
+//
+// MatrixType = chase::matrix::PseudoHermitianMatrix<T, GPU> selects the pseudo-Hermitian (BSE) problem class on any
+// of the layouts (the reference: PseudoHermitianBlockBlockMatrix / PseudoHermitianBlockCyclicMatrix, block-block
+// multivectors only, pchase_gpu.hpp:903-945, 1068-1330): panels hold 2 (nev+nex) columns; H x is formed with the same
+// two local products through H = S H^H S (S = sign flip of the rows whose global index is in the lower half);
+// K-conjugation exchanges the two halves of full-length copies (all-gather inside the grid column) instead of the
+// reference's pairwise send/recv (distMultiVector.hpp:1879-2060).
 #pragma once
 #include "algorithm.hpp"
 #include "chase_gpu.hpp"
@@ -42,24 +49,31 @@ namespace chase
 namespace Impl
 {
 
-template <class T>
+template <class T, class MatrixType = chase::matrix::Matrix<T, chase::platform::GPU>>
 class pChASEGPU : public ChaseBase<T>
 {
     using R = Base<T>;
     using KK = b200::K<T>;
     static constexpr bool kCplx = is_complex_t<T>::value;
+    static constexpr bool kPseudo =
+        std::is_same<MatrixType, chase::matrix::PseudoHermitianMatrix<T, chase::platform::GPU>>::value;
+    static_assert(!kPseudo || kCplx, "pseudo-Hermitian (BSE) problems are complex (reference: c/z only)");
 
 public:
     // H: this rank's local block (m_loc x n_loc, column-major, ldh); V: this rank's rows of the start / result
     // block (m_loc x (nev+nex), ldv); mb / nb: block-cyclic block sizes, 0 = the reference's block layout.
     pChASEGPU(std::size_t N, std::size_t nev, std::size_t nex, const b200::WorldComm& world, int dim0, int dim1,
               char grid_major, std::size_t mb, std::size_t nb, T* H, std::size_t ldh, T* V, std::size_t ldv, R* ritzv)
-        : N_(N), nev_(nev), nex_(nex), nevex_(nev + nex), H_(H), ldh_(ldh), V_(V), ldvh_(ldv), ritzv_(ritzv),
+        : N_(N), nev_(nev), nex_(nex), nevex_(nev + nex), nc_(kPseudo ? 2 * (nev + nex) : nev + nex), H_(H), ldh_(ldh),
+          V_(V), ldvh_(ldv), ritzv_(ritzv),
           grid_(b200::Grid2D::make(dim0, dim1, grid_major, world.rank, world.size)), comm_(world, grid_),
           Dr_((int64_t)N, dim0, (int64_t)mb), Dc_((int64_t)N, dim1, (int64_t)nb), config_(N, nev, nex)
     {
-        if (N == 0 || nevex_ == 0 || nevex_ > N)
-            throw std::invalid_argument("pChASEGPU: need 0 < nev+nex <= N");
+        if (N == 0 || nevex_ == 0 || nc_ > N)
+            throw std::invalid_argument(kPseudo ? "pChASEGPU: need 0 < 2 (nev+nex) <= N"
+                                                : "pChASEGPU: need 0 < nev+nex <= N");
+        if (kPseudo && N % 2 != 0)
+            throw std::invalid_argument("pChASEGPU: a pseudo-Hermitian matrix has even order");
         m_loc_ = (std::size_t)Dr_.local_size(grid_.i);
         n_loc_ = (std::size_t)Dc_.local_size(grid_.j);
         if (ldh < m_loc_ || ldv < m_loc_)
@@ -69,29 +83,39 @@ public:
         ldv_ = roundup(std::max<std::size_t>((std::size_t)Dr_.max_local_size(), 1), 16);
         ldw_ = roundup(std::max<std::size_t>((std::size_t)Dc_.max_local_size(), 1), 16);
         ldn_ = roundup(N_, 16);
-        ldg_ = roundup(nevex_, 16);
+        ldg_ = roundup(nc_, 16);
         dH_ = alloc<T>(lda_ * std::max<std::size_t>(n_loc_, 1));
-        dV1_ = alloc<T>(ldv_ * nevex_);
-        dV2_ = alloc<T>(ldv_ * nevex_);
-        dVs_ = alloc<T>(ldv_ * nevex_);
+        dV1_ = alloc<T>(ldv_ * nc_);
+        dV2_ = alloc<T>(ldv_ * nc_);
+        dVs_ = alloc<T>(ldv_ * nc_);
         for (auto& w : dW_)
-            w = alloc<T>(ldw_ * nevex_);
-        gath_elems_ = std::max((std::size_t)grid_.r * ldv_, (std::size_t)grid_.c * ldw_) * nevex_;
+            w = alloc<T>(ldw_ * nc_);
+        gath_elems_ = std::max((std::size_t)grid_.r * ldv_, (std::size_t)grid_.c * ldw_) * nc_;
         dGath_ = alloc<T>(gath_elems_);
-        dG_ = alloc<T>(ldg_ * nevex_);
-        dZ_ = alloc<T>(ldg_ * nevex_);
-        heev_ws_bytes_ = chase_b200_heev_ws_bytes((int64_t)nevex_, kCplx ? 1 : 0);
+        dG_ = alloc<T>(ldg_ * nc_);
+        dZ_ = alloc<T>(ldg_ * nc_);
+        if (kPseudo)
+        {
+            dM_ = alloc<T>(ldg_ * nc_);
+            dRinv_ = alloc<T>(ldg_ * nc_);
+            dT_ = alloc<T>(ldg_ * nc_);
+            dFull_ = alloc<T>(ldn_ * nevex_); // full-length copies of one half for the K-conjugation
+            ones_ = alloc<double>(nc_);
+            std::vector<double> one(nc_, 1.0);
+            CB2_CHECK(cudaMemcpy(ones_, one.data(), nc_ * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        heev_ws_bytes_ = chase_b200_heev_ws_bytes((int64_t)nc_, kCplx ? 1 : 0);
         heev_ws_ = alloc<unsigned char>(heev_ws_bytes_);
-        trsm_ws_bytes_ = chase_b200_trsm_ws_bytes((int64_t)nevex_, (int)sizeof(T));
+        trsm_ws_bytes_ = chase_b200_trsm_ws_bytes((int64_t)nc_, (int)sizeof(T));
         trsm_ws_ = alloc<unsigned char>(trsm_ws_bytes_);
-        splitk_ws_bytes_ = std::max<std::size_t>(std::size_t(64) << 20, 4 * nevex_ * nevex_ * 16);
+        splitk_ws_bytes_ = std::max<std::size_t>(std::size_t(64) << 20, 4 * nc_ * nc_ * 16);
         splitk_ws_ = alloc<unsigned char>(splitk_ws_bytes_);
-        dTheta_ = alloc<double>(nevex_);
-        dNorms_ = alloc<double>(nevex_);
+        dTheta_ = alloc<double>(nc_);
+        dNorms_ = alloc<double>(nc_);
         dInfo_ = alloc<int>(4);
-        dIdx_ = alloc<int>(2 * nevex_);
-        resid_.assign(nevex_, R(0));
-        perm_.resize(nevex_);
+        dIdx_ = alloc<int>(2 * nc_);
+        resid_.assign(nc_, R(0));
+        perm_.resize(nc_);
         reset_perm();
         build_maps();
         const char* e = std::getenv("CHASE_B200_DEVICE_RNG");
@@ -115,13 +139,13 @@ public:
         if (random && device_rng_)
         {
             // layout-independent Philox block (same matrix as the single-GPU backend draws)
-            CB2_KCHECK(KK::rng_normal_rows((int64_t)m_loc_, (int64_t)nevex_, map_full2v_, (int64_t)N_, dV1_,
+            CB2_KCHECK(KK::rng_normal_rows((int64_t)m_loc_, (int64_t)nc_, map_full2v_, (int64_t)N_, dV1_,
                                            (int64_t)ldv_, 24141ull, stream_));
         }
         else if (random && dV0_ != nullptr)
         {
             // the reference stream is a pure function of (N, nev+nex, T): generated once, then kept on the device
-            CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)nevex_, dV0_, (int64_t)ldv_, dV1_, (int64_t)ldv_, stream_));
+            CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)nc_, dV0_, (int64_t)ldv_, dV1_, (int64_t)ldv_, stream_));
         }
         else
         {
@@ -131,7 +155,7 @@ public:
                 std::mt19937 gen(1337.0);
                 std::normal_distribution<> d;
                 const auto segs = Dr_.segments(grid_.i);
-                for (std::size_t j = 0; j < nevex_; ++j)
+                for (std::size_t j = 0; j < nc_; ++j)
                 {
                     std::size_t s = 0;
                     for (int64_t g = 0; g < (int64_t)N_; ++g)
@@ -145,15 +169,18 @@ public:
                 }
             }
             if (m_loc_ > 0)
-                CB2_CHECK(cudaMemcpy2DAsync(dV1_, ldv_ * sizeof(T), V_, ldvh_ * sizeof(T), m_loc_ * sizeof(T), nevex_,
+                CB2_CHECK(cudaMemcpy2DAsync(dV1_, ldv_ * sizeof(T), V_, ldvh_ * sizeof(T), m_loc_ * sizeof(T), nc_,
                                             cudaMemcpyHostToDevice, stream_));
             if (random)
             {
-                dV0_ = alloc<T>(ldv_ * nevex_);
-                CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)nevex_, dV1_, (int64_t)ldv_, dV0_, (int64_t)ldv_, stream_));
+                dV0_ = alloc<T>(ldv_ * nc_);
+                CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)nc_, dV1_, (int64_t)ldv_, dV0_, (int64_t)ldv_, stream_));
             }
         }
-        CB2_KCHECK(KK::lacpy((int64_t)ldv_, (int64_t)nevex_, dV1_, (int64_t)ldv_, dV2_, (int64_t)ldv_, stream_));
+        if (random && kPseudo) // damp the lower (de-excitation) block: T(0.001), pchase_gpu.hpp:700-716
+            CB2_KCHECK(KK::scale_rows_map((int64_t)m_loc_, (int64_t)nc_, map_full2v_, (int64_t)(N_ / 2), dV1_,
+                                          (int64_t)ldv_, (double)(R)0.001, stream_));
+        CB2_KCHECK(KK::lacpy((int64_t)ldv_, (int64_t)nc_, dV1_, (int64_t)ldv_, dV2_, (int64_t)ldv_, stream_));
         if (!(keep_device_matrix_ && matrix_on_device_) && m_loc_ > 0 && n_loc_ > 0)
         {
             CB2_CHECK(cudaMemcpy2DAsync(dH_, lda_ * sizeof(T), H_, ldh_ * sizeof(T), m_loc_ * sizeof(T), n_loc_,
@@ -190,13 +217,46 @@ public:
         next_ = (next_ == NextOp::bAc) ? NextOp::cAb : NextOp::bAc;
     }
 
-    void HEMM_H2(std::size_t, T, T, T, std::size_t, std::size_t = 0) override
+    // V2[cols] <- alpha H (H V1[cols]) + beta V2[cols] + gamma V1[cols]; swap (pchase_gpu.hpp:903-945).  One round
+    // trip through the row layout: W = H V1 = S (A^H (S V1)) with the A^H product, V2 = alpha A W + beta V2 with the A
+    // product.  Columns as in ChASEGPU::HEMM_H2: [locked_ + offset_left, locked_ + block - offset_right).
+    void HEMM_H2(std::size_t block, T alpha, T beta, T gamma, std::size_t offset_left,
+                 std::size_t offset_right = 0) override
     {
-        throw std::runtime_error("chase_b200: pseudo-Hermitian HEMM_H2 is not implemented yet");
+        if (!kPseudo)
+            throw std::runtime_error("chase_b200: HEMM_H2 needs MatrixType = PseudoHermitianMatrix");
+        flush_perm();
+        resid_ready_ = false;
+        std::size_t ncols = (offset_right < block) ? block - offset_right : 0;
+        ncols = (offset_left < ncols) ? ncols - offset_left : 0;
+        if (ncols > 0)
+        {
+            const std::size_t c0 = offset_left + locked_;
+            T* in = dV1_ + c0 * ldv_;
+            T* out = dV2_ + c0 * ldv_;
+            T* tmp = dW_[0] + c0 * ldw_;
+            times_H_v2w(in, tmp, ncols);
+            hemm_w2v(alpha, tmp, beta, out, ncols);
+            CB2_KCHECK(KK::axpy_cols((int64_t)m_loc_, (int64_t)ncols, ones_, b200::re_of(gamma), b200::im_of(gamma), in,
+                                     (int64_t)ldv_, out, (int64_t)ldv_, stream_));
+            hemm_cols_ += 2 * ncols;
+        }
+        std::swap(dV1_, dV2_);
     }
-    void ApplyKconjugate(std::size_t) override
+
+    // V1[:, 2 nevex - locked - block ...) <- K-conjugates of V1[:, locked ... locked + block): the partner of row g
+    // is row g +- N/2, in general on another rank, so the halves are exchanged on full-length copies
+    void ApplyKconjugate(std::size_t block) override
     {
-        throw std::runtime_error("chase_b200: pseudo-Hermitian ApplyKconjugate is not implemented yet");
+        if (!kPseudo)
+            return;
+        flush_perm();
+        if (block == 0)
+            return;
+        const std::size_t col_second = nc_ - locked_ - block;
+        v_to_full(dV1_ + locked_ * ldv_, dFull_, block);
+        CB2_KCHECK(KK::kconj((int64_t)N_, (int64_t)block, dFull_, (int64_t)ldn_, dFull_, (int64_t)ldn_, stream_));
+        full_to_v(dFull_, dV1_ + col_second * ldv_, block);
     }
 
     void QR(std::size_t /*fixednev*/, R cond) override
@@ -204,6 +264,20 @@ public:
         flush_perm();
         resid_ready_ = false;
         CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)locked_, dV1_, (int64_t)ldv_, dV2_, (int64_t)ldv_, stream_));
+        if (kPseudo)
+        {
+            // [L+ | active | L-] -> orthogonalise [S L+ | S L- | active] (pchase_gpu.hpp:1068-1120)
+            const std::size_t act = nc_ - 2 * locked_;
+            const int64_t m = (int64_t)m_loc_, ld = (int64_t)ldv_;
+            CB2_KCHECK(KK::lacpy(m, (int64_t)locked_, dV1_ + (nc_ - locked_) * ldv_, ld, dV2_ + (nc_ - locked_) * ldv_, ld,
+                                 stream_));
+            CB2_KCHECK(KK::lacpy(m, (int64_t)locked_, dV1_, ld, dVs_, ld, stream_));
+            CB2_KCHECK(KK::lacpy(m, (int64_t)locked_, dV1_ + (nc_ - locked_) * ldv_, ld, dVs_ + locked_ * ldv_, ld,
+                                 stream_));
+            CB2_KCHECK(KK::lacpy(m, (int64_t)act, dV1_ + locked_ * ldv_, ld, dVs_ + 2 * locked_ * ldv_, ld, stream_));
+            std::swap(dV1_, dVs_);
+            flip_v(dV1_, 2 * locked_);
+        }
 
         int disable = config_.DoCholQR() ? 0 : 1;
         if (const char* s = std::getenv("CHASE_DISABLE_CHOLQR"))
@@ -247,6 +321,17 @@ public:
                                          ") and no Householder fallback is available yet");
         }
         qr_log_.push_back(last_qr_);
+        if (kPseudo)
+        {
+            const std::size_t act = nc_ - 2 * locked_;
+            const int64_t m = (int64_t)m_loc_, ld = (int64_t)ldv_;
+            CB2_KCHECK(KK::lacpy(m, (int64_t)act, dV1_ + 2 * locked_ * ldv_, ld, dVs_ + locked_ * ldv_, ld, stream_));
+            std::swap(dV1_, dVs_);
+            CB2_KCHECK(KK::lacpy(m, (int64_t)locked_, dV2_ + (nc_ - locked_) * ldv_, ld, dV1_ + (nc_ - locked_) * ldv_, ld,
+                                 stream_));
+            if (locked_ == 0) // both panels hold the orthonormal block (LanczosDos reads the second one)
+                CB2_KCHECK(KK::lacpy(m, (int64_t)nc_, dV1_, ld, dV2_, ld, stream_));
+        }
         CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)locked_, dV2_, (int64_t)ldv_, dV1_, (int64_t)ldv_, stream_));
     }
 
@@ -256,6 +341,11 @@ public:
         resid_ready_ = false;
         if (block == 0)
             return;
+        if (kPseudo)
+        {
+            rr_pseudo(ritzv, block);
+            return;
+        }
         T* Q = dV1_ + locked_ * ldv_;
         T* W1 = dW_[0] + locked_ * ldw_;
         T* W2 = dW_[1] + locked_ * ldw_;
@@ -321,7 +411,10 @@ public:
             CB2_CHECK(cudaMemcpyAsync(dTheta_, th.data(), k * sizeof(double), cudaMemcpyHostToDevice, stream_));
             T* Vb = dV1_ + locked_ * ldv_;
             T* E = dW_[2] + locked_ * ldw_;
-            hemm_v2w(T(1), Vb, T(0), Rm, k);
+            if (kPseudo)
+                times_H_v2w(Vb, Rm, k); // H is not Hermitian: H V = S A^H S V
+            else
+                hemm_v2w(T(1), Vb, T(0), Rm, k);
             redistribute_v2w(Vb, E, k);
             CB2_KCHECK(KK::axpy_cols((int64_t)n_loc_, (int64_t)k, dTheta_, -1.0, 0.0, E, (int64_t)ldw_, Rm,
                                      (int64_t)ldw_, stream_));
@@ -345,14 +438,20 @@ public:
         lanczosIter_ = M;
         numLanczos_ = 1;
         std::vector<R> theta(M), tau(M), rv(M * M);
-        run_lanczos(M, 1, upperb, theta.data(), tau.data(), rv.data(), false);
+        if (kPseudo)
+            run_lanczos_pseudo(M, 1, upperb, theta.data(), tau.data(), rv.data(), false);
+        else
+            run_lanczos(M, 1, upperb, theta.data(), tau.data(), rv.data(), false);
     }
 
     void Lanczos(std::size_t M, std::size_t numvec, R* upperb, R* ritzv, R* Tau, R* ritzV) override
     {
         lanczosIter_ = M;
         numLanczos_ = numvec;
-        run_lanczos(M, numvec, upperb, ritzv, Tau, ritzV, true);
+        if (kPseudo)
+            run_lanczos_pseudo(M, numvec, upperb, ritzv, Tau, ritzV, true);
+        else
+            run_lanczos(M, numvec, upperb, ritzv, Tau, ritzV, true);
     }
 
     void LanczosDos(std::size_t idx, std::size_t m, T* ritzVc) override
@@ -414,9 +513,48 @@ public:
         is_sym_ = std::sqrt(nr[0]) <= tol * std::sqrt(nr[1]);
         return is_sym_;
     }
-    bool isSym() override { return true; }
-    bool checkPseudoHermicityEasy() override { return false; }
-    bool isPseudoHerm() override { return false; }
+    bool isSym() override { return !kPseudo; }
+    // S H x == H^H S x on a random vector (the distributed analogue of the single-GPU check)
+    bool checkPseudoHermicityEasy() override
+    {
+        if (!kPseudo)
+            return false;
+        flush_perm();
+        if (!matrix_on_device_ && m_loc_ > 0 && n_loc_ > 0)
+        {
+            CB2_CHECK(cudaMemcpy2DAsync(dH_, lda_ * sizeof(T), H_, ldh_ * sizeof(T), m_loc_ * sizeof(T), n_loc_,
+                                        cudaMemcpyHostToDevice, stream_));
+            matrix_on_device_ = true;
+        }
+        T* x = dVs_;
+        CB2_KCHECK(KK::rng_normal_rows((int64_t)m_loc_, 1, map_full2v_, (int64_t)N_, x, (int64_t)ldv_, 777ull, stream_));
+        T* y1 = dW_[2]; // A^H (S x)                (row layout)
+        T* xw = dW_[3];
+        flip_v(x, 1);
+        hemm_v2w(T(1), x, T(0), y1, 1);
+        flip_v(x, 1);
+        redistribute_v2w(x, xw, 1);
+        T* y2 = dVs_ + ldv_; // S (A x)             (column layout)
+        hemm_w2v(T(1), xw, T(0), y2, 1);
+        flip_v(y2, 1);
+        T* y2w = dW_[3] + ldw_;
+        redistribute_v2w(y2, y2w, 1);
+        double m1[2] = {-1.0, 0.0};
+        CB2_CHECK(cudaMemcpyAsync(dTheta_, m1, sizeof(double), cudaMemcpyHostToDevice, stream_));
+        CB2_KCHECK(KK::colnorms((int64_t)n_loc_, 1, y1, (int64_t)ldw_, dNorms_ + 1, 0, stream_));
+        CB2_KCHECK(KK::axpy_cols((int64_t)n_loc_, 1, dTheta_, 1.0, 0.0, y2w, (int64_t)ldw_, y1, (int64_t)ldw_, stream_));
+        CB2_KCHECK(KK::colnorms((int64_t)n_loc_, 1, y1, (int64_t)ldw_, dNorms_, 0, stream_));
+        if (grid_.c > 1)
+            comm_.allreduce_sum(dNorms_, 2, comm_.row(), stream_);
+        if (grid_.r > 1)
+            comm_.broadcast(dNorms_, 2, 0, comm_.col(), stream_);
+        double nr[2];
+        CB2_CHECK(cudaMemcpyAsync(nr, dNorms_, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        const double tol = (sizeof(R) == 8) ? 1e-10 : 1e-4;
+        return std::sqrt(nr[0]) <= tol * std::sqrt(nr[1]);
+    }
+    bool isPseudoHerm() override { return kPseudo; }
     void symOrHermMatrix(char) override
     {
         throw std::runtime_error("chase_b200: symOrHermMatrix is not available for distributed matrices yet");
@@ -426,7 +564,7 @@ public:
     {
         flush_perm();
         if (m_loc_ > 0)
-            CB2_CHECK(cudaMemcpy2DAsync(V_, ldvh_ * sizeof(T), dV1_, ldv_ * sizeof(T), m_loc_ * sizeof(T), nevex_,
+            CB2_CHECK(cudaMemcpy2DAsync(V_, ldvh_ * sizeof(T), dV1_, ldv_ * sizeof(T), m_loc_ * sizeof(T), nc_,
                                         cudaMemcpyDeviceToHost, stream_));
         CB2_CHECK(cudaStreamSynchronize(stream_));
     }
@@ -436,7 +574,7 @@ public:
     std::size_t GetNex() override { return nex_; }
     std::size_t GetLanczosIter() override { return lanczosIter_; }
     std::size_t GetNumLanczos() override { return numLanczos_; }
-    std::size_t GetRitzvBlockSize() const override { return nevex_; }
+    std::size_t GetRitzvBlockSize() const override { return nc_; }
     R* GetRitzv() override { return ritzv_; }
     R* GetResid() override { return resid_.data(); }
     ChaseConfig<T>& GetConfig() override { return config_; }
@@ -510,8 +648,9 @@ private:
         // full-length vectors out of gathered column-layout / row-layout pieces
         map_v2full_ = upload_map(expand(b200::redistribution_list(Dr_, (int64_t)ldv_, full, 0), N_));
         map_w2full_ = upload_map(expand(b200::redistribution_list(Dc_, (int64_t)ldw_, full, 0), N_));
-        // my column-layout rows out of a full-length vector (= their global indices)
+        // my column-layout rows out of a full-length vector (= their global indices); same for the row layout
         map_full2v_ = upload_map(Dr_.global_indices(grid_.i));
+        map_full2w_ = upload_map(Dc_.global_indices(grid_.j));
         // local copies of global diagonal entries
         std::vector<int64_t> lin;
         const auto gcols = Dc_.global_indices(grid_.j);
@@ -591,7 +730,7 @@ private:
 
     void reset_perm()
     {
-        for (std::size_t i = 0; i < nevex_; ++i)
+        for (std::size_t i = 0; i < nc_; ++i)
             perm_[i] = (int)i;
         perm_dirty_ = false;
     }
@@ -600,7 +739,7 @@ private:
         if (!perm_dirty_)
             return;
         std::vector<int> src, dst;
-        for (std::size_t j = 0; j < nevex_; ++j)
+        for (std::size_t j = 0; j < nc_; ++j)
             if (perm_[j] != (int)j)
             {
                 src.push_back(perm_[j]);
@@ -626,13 +765,13 @@ private:
     // column, replicated Cholesky, local TRSM
     int chol_round(bool shifted, double shift_boost)
     {
-        const int64_t n = (int64_t)nevex_;
+        const int64_t n = (int64_t)nc_;
         CB2_KCHECK(KK::gemm(1, 0, n, n, (int64_t)m_loc_, 1.0, 0.0, dV1_, (int64_t)ldv_, dV1_, (int64_t)ldv_, 0.0, 0.0,
                             dG_, (int64_t)ldg_, 1, splitk_ws_, splitk_ws_bytes_, stream_));
         if (grid_.r > 1)
-            comm_.allreduce_sum(dG_, ldg_ * nevex_, comm_.col(), stream_);
+            comm_.allreduce_sum(dG_, ldg_ * nc_, comm_.col(), stream_);
         if (grid_.c > 1)
-            comm_.broadcast(dG_, ldg_ * nevex_, 0, comm_.row(), stream_);
+            comm_.broadcast(dG_, ldg_ * nc_, 0, comm_.row(), stream_);
         if (shifted)
         {
             const double scale = (sizeof(R) == 8) ? std::sqrt((double)N_) * 2.220446049250313e-16
@@ -662,16 +801,157 @@ private:
         return chol_round(false, 0.0);
     }
 
-    // Lanczos with the numvec vectors replicated in full length on every rank: A v is the only distributed step
-    // (local A_loc^H x, allreduce inside the grid column, all-gather inside the grid row); the fused vector update
-    // of the single-GPU backend then runs identically everywhere.  Formulas: cpu/lanczos.hpp:45-209.
-    void run_lanczos(std::size_t M, std::size_t numvec, R* upperb, R* Theta, R* Tau, R* ritzV, bool multi)
+    // S X on a distributed panel: negate the local rows whose global index lies in the lower half
+    void flip_v(T* X, std::size_t k)
+    {
+        CB2_KCHECK(KK::scale_rows_map((int64_t)m_loc_, (int64_t)k, map_full2v_, (int64_t)(N_ / 2), X, (int64_t)ldv_, -1.0,
+                                      stream_));
+    }
+    void flip_w(T* X, std::size_t k)
+    {
+        CB2_KCHECK(KK::scale_rows_map((int64_t)n_loc_, (int64_t)k, map_full2w_, (int64_t)(N_ / 2), X, (int64_t)ldw_, -1.0,
+                                      stream_));
+    }
+    // W (row layout) <- H V for the pseudo-Hermitian H: H = S H^H S, so the A^H product of the Hermitian path serves
+    void times_H_v2w(T* V, T* W, std::size_t k)
+    {
+        flip_v(V, k);
+        hemm_v2w(T(1), V, T(0), W, k);
+        flip_v(V, k);
+        flip_w(W, k);
+    }
+
+    // Distributed rayleighRitz_v2 (reference linalg/internal/nccl/pseudo_hermitian_rayleighRitz.hpp; statement:
+    // cpu/rayleighRitz.hpp:284-392) on Q = V1[:, locked_ ... locked_ + 2 block): the two N-long contractions are local
+    // GEMMs + one allreduce each, the n x n part is replicated (and broadcast from one replica: identical decisions).
+    void rr_pseudo(R* ritzv, std::size_t block)
+    {
+        const std::size_t nn = 2 * block;
+        const int64_t n = (int64_t)nn, ldg = (int64_t)ldg_;
+        T* Q = dV1_ + locked_ * ldv_;
+        T* W1 = dW_[0] + locked_ * ldw_; // S H Q = A^H (S Q)   (row layout)
+        T* W2 = dW_[1] + locked_ * ldw_; // Q                   (row layout)
+        T* SQ = dVs_ + locked_ * ldv_;   // S Q                 (column layout)
+        if (grid_.c > 1)
+            comm_.broadcast(Q, ldv_ * nn, 0, comm_.row(), stream_);
+        CB2_KCHECK(KK::lacpy((int64_t)m_loc_, n, Q, (int64_t)ldv_, SQ, (int64_t)ldv_, stream_));
+        flip_v(SQ, nn);
+        hemm_v2w(T(1), SQ, T(0), W1, nn);
+        redistribute_v2w(Q, W2, nn);
+        // G = Q^H S H Q
+        CB2_KCHECK(KK::gemm(1, 0, n, n, (int64_t)n_loc_, 1.0, 0.0, W2, (int64_t)ldw_, W1, (int64_t)ldw_, 0.0, 0.0, dG_, ldg,
+                            0, splitk_ws_, splitk_ws_bytes_, stream_));
+        if (grid_.c > 1)
+            comm_.allreduce_sum(dG_, ldg_ * nn, comm_.row(), stream_);
+        if (grid_.r > 1)
+            comm_.broadcast(dG_, ldg_ * nn, 0, comm_.col(), stream_);
+        // M0 = Q^H S Q (= I - 2 Q2^H Q2 for orthonormal Q)
+        CB2_KCHECK(KK::gemm(1, 0, n, n, (int64_t)m_loc_, 1.0, 0.0, Q, (int64_t)ldv_, SQ, (int64_t)ldv_, 0.0, 0.0, dM_, ldg,
+                            0, splitk_ws_, splitk_ws_bytes_, stream_));
+        if (grid_.r > 1)
+            comm_.allreduce_sum(dM_, ldg_ * nn, comm_.col(), stream_);
+        if (grid_.c > 1)
+            comm_.broadcast(dM_, ldg_ * nn, 0, comm_.row(), stream_);
+        CB2_CHECK(cudaMemsetAsync(dInfo_, 0, sizeof(int), stream_));
+        CB2_KCHECK(KK::potrf(n, dG_, ldg, dInfo_, stream_));
+        int info = 0;
+        CB2_CHECK(cudaMemcpyAsync(&info, dInfo_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        if (info != 0)
+            throw std::runtime_error("chase_b200: Q^H S H Q is not positive definite in the pseudo-Hermitian RR "
+                                     "(potrf info=" + std::to_string(info) + "): S H must be positive definite");
+        CB2_CHECK(cudaMemsetAsync(dT_, 0, ldg_ * nn * sizeof(T), stream_));
+        CB2_KCHECK(KK::shift_diag(n, dT_, ldg, 1.0, stream_));
+        CB2_KCHECK(KK::trsm(n, n, dG_, ldg, dT_, ldg, dRinv_, ldg, trsm_ws_, trsm_ws_bytes_, stream_));
+        // M = -R^-H M0 R^-1
+        CB2_KCHECK(KK::gemm(0, 0, n, n, n, 1.0, 0.0, dM_, ldg, dRinv_, ldg, 0.0, 0.0, dT_, ldg, 0, nullptr, 0, stream_));
+        CB2_KCHECK(KK::gemm(1, 0, n, n, n, -1.0, 0.0, dRinv_, ldg, dT_, ldg, 0.0, 0.0, dM_, ldg, 0, nullptr, 0,
+                            stream_));
+        std::vector<double> w(nn);
+        int sweeps = 0;
+        const int rc = KK::heev(n, dM_, ldg, dZ_, ldg, w.data(), heev_ws_, heev_ws_bytes_, &sweeps, stream_);
+        if (rc != 0)
+            throw std::runtime_error("chase_b200: Hermitian eigensolver failed in the pseudo-Hermitian RR (rc=" +
+                                     std::to_string(rc) + ")");
+        heev_sweeps_ += sweeps;
+        for (std::size_t i = 0; i < nn; ++i)
+            ritzv[i] = R(1.0) / (R)(-w[i]);
+        CB2_KCHECK(KK::gemm(0, 0, n, (int64_t)block, n, 1.0, 0.0, dRinv_, ldg, dZ_, ldg, 0.0, 0.0, dT_, ldg, 0, nullptr,
+                            0, stream_));
+        CB2_KCHECK(KK::normalize_cols(n, (int64_t)block, dT_, ldg, stream_));
+        CB2_KCHECK(KK::gemm(0, 0, (int64_t)m_loc_, (int64_t)block, n, 1.0, 0.0, Q, (int64_t)ldv_, dT_, ldg, 0.0, 0.0,
+                            dV2_ + locked_ * ldv_, (int64_t)ldv_, 0, nullptr, 0, stream_));
+        std::swap(dV1_, dV2_);
+    }
+
+    // Lanczos in the S H inner product on full-length replicated vectors (cpu/lanczos.hpp:332-516); H x = S A^H S x
+    // is the only distributed step.
+    void run_lanczos_pseudo(std::size_t M, std::size_t numvec, R* upperb, R* Theta, R* Tau, R* ritzV, bool multi)
     {
         flush_perm();
         resid_ready_ = false;
         if (M > 48)
             throw std::runtime_error("chase_b200: Lanczos with more than 48 steps is not supported yet");
         const int nv = (int)numvec, m = (int)M;
+        ensure_lanczos_buffers(M, numvec);
+        T* v0 = lan_v_;
+        T* v1 = lan_v_ + ldn_ * numvec;
+        T* v2 = lan_v_ + 2 * ldn_ * numvec;
+        const int64_t N = (int64_t)N_, half = (int64_t)(N_ / 2), ldn = (int64_t)ldn_;
+        T* xloc = dVs_;
+        T* ypart = dW_[2];
+        auto matvec = [&](T* x, T* y)
+        {
+            CB2_KCHECK(KK::scale_rows(N - half, nv, x + half, ldn, -1.0, stream_));
+            full_to_v(x, xloc, numvec);
+            CB2_KCHECK(KK::scale_rows(N - half, nv, x + half, ldn, -1.0, stream_));
+            CB2_KCHECK(KK::gemv_conjt((int64_t)m_loc_, (int64_t)n_loc_, dH_, (int64_t)lda_, xloc, (int64_t)ldv_, nv,
+                                      ypart, (int64_t)ldw_, stream_));
+            if (grid_.r > 1)
+                comm_.allreduce_sum(ypart, ldw_ * numvec, comm_.col(), stream_);
+            w_to_full(ypart, y, numvec);
+            CB2_KCHECK(KK::scale_rows(N - half, nv, y + half, ldn, -1.0, stream_));
+        };
+        CB2_CHECK(cudaMemsetAsync(lan_d_, 0, M * numvec * sizeof(double), stream_));
+        CB2_CHECK(cudaMemsetAsync(lan_e_, 0, M * numvec * sizeof(double), stream_));
+        v_to_full(dV1_, v1, numvec);
+        matvec(v1, v2);
+        CB2_KCHECK(KK::lanczos_pseudo_norm(N, nv, -1, m, v1, v2, ldn, lan_e_, lan_rb_, stream_));
+        for (int k = 0; k < m; ++k)
+        {
+            if (multi)
+                full_to_v(v1 + (std::size_t)(nv - 1) * ldn_, dV1_ + (std::size_t)k * ldv_, 1);
+            CB2_KCHECK(KK::lanczos_pseudo_step(N, nv, k, m, v0, v1, v2, ldn, lan_d_, lan_rb_, stream_));
+            if (k == m - 1)
+                break;
+            T* t = v0;
+            v0 = v1;
+            v1 = v2;
+            v2 = t;
+            matvec(v1, v2);
+            CB2_KCHECK(KK::lanczos_pseudo_norm(N, nv, k, m, v1, v2, ldn, lan_e_, lan_rb_, stream_));
+        }
+        if (multi)
+            full_to_v(v1, dV1_, numvec);
+        CB2_KCHECK(chase_b200_tridiag_eig(m, nv, lan_d_, lan_e_, m, lan_w_, lan_Z_, stream_));
+        std::vector<double> w(M * numvec), Z(M * M * numvec);
+        CB2_CHECK(cudaMemcpyAsync(w.data(), lan_w_, w.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaMemcpyAsync(Z.data(), lan_Z_, Z.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        for (std::size_t i = 0; i < numvec; ++i)
+            for (std::size_t k = 0; k < M; ++k)
+            {
+                Theta[k + M * i] = (R)w[i * M + k];
+                const R z0 = (R)Z[i * M * M + 0 + k * M];
+                Tau[k + i * M] = std::abs(z0) * std::abs(z0);
+            }
+        for (std::size_t q = 0; q < M * M; ++q)
+            ritzV[q] = (R)Z[(numvec - 1) * M * M + q];
+        *upperb = Theta[M - 1];
+    }
+
+    void ensure_lanczos_buffers(std::size_t M, std::size_t numvec)
+    {
         if (lan_nv_ < numvec)
         {
             lan_v_ = alloc<T>(3 * ldn_ * numvec);
@@ -686,6 +966,19 @@ private:
             lan_rb_ = alloc<double>(numvec + 1);
             lan_m_ = M * numvec;
         }
+    }
+
+    // Lanczos with the numvec vectors replicated in full length on every rank: A v is the only distributed step
+    // (local A_loc^H x, allreduce inside the grid column, all-gather inside the grid row); the fused vector update
+    // of the single-GPU backend then runs identically everywhere.  Formulas: cpu/lanczos.hpp:45-209.
+    void run_lanczos(std::size_t M, std::size_t numvec, R* upperb, R* Theta, R* Tau, R* ritzV, bool multi)
+    {
+        flush_perm();
+        resid_ready_ = false;
+        if (M > 48)
+            throw std::runtime_error("chase_b200: Lanczos with more than 48 steps is not supported yet");
+        const int nv = (int)numvec, m = (int)M;
+        ensure_lanczos_buffers(M, numvec);
         T* v0 = lan_v_;
         T* v1 = lan_v_ + ldn_ * numvec;
         T* v2 = lan_v_ + 2 * ldn_ * numvec;
@@ -742,6 +1035,7 @@ private:
     }
 
     std::size_t N_, nev_, nex_, nevex_;
+    std::size_t nc_; // columns of the panels: nev+nex, or 2 (nev+nex) for pseudo-Hermitian problems
     T* H_;
     std::size_t ldh_;
     T* V_;
@@ -756,13 +1050,15 @@ private:
     T *dH_ = nullptr, *dV1_ = nullptr, *dV2_ = nullptr, *dVs_ = nullptr, *dGath_ = nullptr, *dG_ = nullptr,
       *dZ_ = nullptr;
     T* dW_[4] = {nullptr, nullptr, nullptr, nullptr};
+    T *dM_ = nullptr, *dRinv_ = nullptr, *dT_ = nullptr, *dFull_ = nullptr; // pseudo-Hermitian only
+    double* ones_ = nullptr;
     T* dV0_ = nullptr; // device copy of this rank's rows of the reference start block (parity mode)
     unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr;
     std::size_t heev_ws_bytes_ = 0, trsm_ws_bytes_ = 0, splitk_ws_bytes_ = 0;
     double *dTheta_ = nullptr, *dNorms_ = nullptr;
     int *dInfo_ = nullptr, *dIdx_ = nullptr;
     int64_t *map_v2w_ = nullptr, *map_v2full_ = nullptr, *map_w2full_ = nullptr, *map_full2v_ = nullptr,
-            *diag_lin_ = nullptr;
+            *map_full2w_ = nullptr, *diag_lin_ = nullptr;
     std::size_t ndiag_ = 0;
     T* lan_v_ = nullptr;
     double *lan_d_ = nullptr, *lan_e_ = nullptr, *lan_w_ = nullptr, *lan_Z_ = nullptr, *lan_rb_ = nullptr;

@@ -122,6 +122,10 @@ extern "C"
        pseudo-Hermitian path (reference cuda/flipSign.cu, chase_gpu.hpp:752-782); a = 1e-3 is the start-vector        \
        damping of the lower block (chase_gpu.hpp:518-529). */                                                         \
     int chase_b200_scale_rows_##X(int64_t nrows, int64_t cols, void* Xm, int64_t ldx, double a, void* stream);        \
+    /* Same on a row-split (distributed) panel: X[i, :cols] *= a for the local rows whose global index               \
+       grow_dev[i] >= g0 (device int64 map, the rows' global indices). */                                             \
+    int chase_b200_scale_rows_map_##X(int64_t rows, int64_t cols, const int64_t* grow_dev, int64_t g0, void* Xm,      \
+                                      int64_t ldx, double a, void* stream);                                           \
     /* K-conjugate partner vectors dst[:, j] = conj([src[rows/2:, j]; src[:rows/2, j]]), rows even, src/dst           \
        disjoint.  Replaces the two lacpy + conjugate kernel of ChASEGPU::ApplyKconjugate (chase_gpu.hpp:718-742). */  \
     int chase_b200_kconj_##X(int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst, int64_t ldd,        \

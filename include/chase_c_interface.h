@@ -128,6 +128,23 @@ extern "C"
     CHASE_B200_DIST_API(z, CHASE_B200_CD, double)
     CHASE_B200_DIST_API(c, CHASE_B200_CF, float)
 
+    /* Distributed pseudo-Hermitian (BSE) problems (reference interface/chase_c_interface.h:105-123, 158-175): same
+       arguments as the Hermitian initialisers; V holds the m local rows of 2 (nev+nex) vectors and ritzv 2 (nev+nex)
+       entries.  While a pseudo solver exists, p?chase_ / p?chase_get_eigenpairs_ / p?chase_finalize_ act on it. */
+#define CHASE_B200_DIST_PSEUDO_API(X, CT, RT)                                                                          \
+    void p##X##chase_init_pseudo_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, CT* V, RT* ritzv,      \
+                                  int* dim0, int* dim1, char* grid_major, MPI_Comm* comm, int* init);                  \
+    void p##X##chase_init_pseudo_internal_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, int* dim0,    \
+                                           int* dim1, char* grid_major, MPI_Comm* comm, int* init);                    \
+    void p##X##chase_init_pseudo_blockcyclic_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H, int* ldh,  \
+                                              CT* V, RT* ritzv, int* dim0, int* dim1, char* grid_major, int* irsrc,    \
+                                              int* icsrc, MPI_Comm* comm, int* init);                                  \
+    void p##X##chase_init_pseudo_blockcyclic_internal_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H,   \
+                                                       int* ldh, int* dim0, int* dim1, char* grid_major, int* irsrc,   \
+                                                       int* icsrc, MPI_Comm* comm, int* init);
+    CHASE_B200_DIST_PSEUDO_API(z, CHASE_B200_CD, double)
+    CHASE_B200_DIST_PSEUDO_API(c, CHASE_B200_CF, float)
+
     /* ---- chase_b200 additions (introspection for parity tests and benchmarks) ---- */
     /* residuals of the last solve (nev+nex values, ordered like ritzv) */
     void dchase_get_resid_(double* resid);

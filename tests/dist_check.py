@@ -78,6 +78,69 @@ def run_case(world, name, grid, layout, major):
                 filtered_vecs=res.filtered_vecs, max_rel_eig=rel, max_resid=float(rr.max()), orth=orth, fails=fails)
 
 
+def run_pseudo_case(world, name, grid, layout, major):
+    """Pseudo-Hermitian (BSE) solve on a grid (p?chase_init_pseudo_[blockcyclic_]) against the golden trace of the
+    serial reference solver (chase_ref_cpu_pz, Solve_pseudo) and the known spectrum."""
+    import torch.distributed as dist
+
+    from tests.test_pseudo_gpu import _golden_spectrum, _matrix
+
+    g = load(name)
+    p = g["problems"][0]
+    N, nev, nex = g["N"], g["nev"], g["nex"]
+    H, _ = _matrix(g)
+    nb = 0 if layout == "block" else 32
+    r, c = grid
+    i, j = cd.grid_coords(r, c, major, world.rank)
+    gr, gc = cd.global_indices(N, r, nb, i), cd.global_indices(N, c, nb, j)
+    with cd.PChASE(world, N, nev, nex, np.asfortranarray(H[np.ix_(gr, gc)]), grid=grid, major=major, mb=nb, nb=nb,
+                   pseudo=True) as s:
+        if "numlanczos" in g:
+            L = s._lib
+            import ctypes
+
+            L.chase_set_num_lanczos_(ctypes.byref(ctypes.c_int(g["numlanczos"])))
+            L.chase_set_lanczos_iter_(ctypes.byref(ctypes.c_int(g["lanczositer"])))
+        res = s.solve(deg=g["deg"], tol=g["tol"], opt="S" if g["opt"] else "N", trace=True)
+    ref, got = parse_trace(p["trace"]), parse_trace(res.trace)
+    fails = []
+    if res.iterations != p["iterations"]:
+        fails.append(f"iterations {res.iterations} != {p['iterations']}")
+    if res.filtered_vecs != p["filtered_vecs"]:
+        fails.append(f"filtered_vecs {res.filtered_vecs} != {p['filtered_vecs']}")
+    if [h[:2] for h in got["hemm_h2"]] != [h[:2] for h in ref["hemm_h2"]]:
+        fails.append("HEMM_H2 schedule differs")
+    if got["locks"] != ref["locks"]:
+        fails.append(f"locks {got['locks']} != {ref['locks']}")
+    if got["applyk"] != ref["applyk"]:
+        fails.append("ApplyKconjugate sequence differs")
+    exact = _golden_spectrum(g)[:nev]
+    rel = float(np.max(np.abs(res.ritzv[:nev] - exact) / exact))
+    relref = float(np.max(np.abs(res.ritzv[:nev] - np.array(p["ritzv"][:nev])) / exact))
+    if max(rel, relref) > 1e-10:
+        fails.append(f"eigenvalues off by {rel:.2e} (exact) / {relref:.2e} (reference)")
+    if not np.all(res.resid[:nev] < 1000 * g["tol"]):
+        fails.append("residuals above tolerance")
+    parts = [None] * world.size
+    if world.size > 1:
+        dist.all_gather_object(parts, (i, j, gr, res.V[:len(gr), :nev]))
+    else:
+        parts = [(i, j, gr, res.V[:len(gr), :nev])]
+    V = np.zeros((N, nev), dtype=H.dtype)
+    for (pi, pj, rows, blk) in parts:
+        if pj == 0:
+            V[rows, :] = blk
+    rr = np.linalg.norm(H @ V - V * res.ritzv[:nev], axis=0)
+    if not (np.all(rr < 1e-7 * np.abs(exact).max()) and np.all(rr > 0)):
+        fails.append(f"recomputed residual max {rr.max():.2e}")
+    for (pi, pj, rows, blk) in parts:
+        if pj != 0 and np.max(np.abs(V[rows, :] - blk)) > 1e-12:
+            fails.append("column-layout replicas differ")
+    return dict(case=name + " (pseudo-Hermitian)", grid=f"{r}x{c}", layout=layout, major=major,
+                iterations=res.iterations, filtered_vecs=res.filtered_vecs, max_rel_eig=rel, max_resid=float(rr.max()),
+                fails=fails)
+
+
 def run_sequence(world, name, grid, layout, major):
     """tests/noinput.cpp-style sequence on a grid: problem 0 random start, then perturbed matrices re-using the
     distributed V / ritzv (mode 'A'); the local host blocks are re-read at every solve."""
@@ -118,6 +181,7 @@ def main():
     ap.add_argument("--grid", default="")
     ap.add_argument("--out", default="")
     ap.add_argument("--no-seq", action="store_true")
+    ap.add_argument("--pseudo-cases", default="pseudo_bse_z_N200,pseudo_synth_z_N600")
     a = ap.parse_args()
     world = cd.World()
     grids = [tuple(int(x) for x in a.grid.split("x"))] if a.grid else [cd.grid_dims(world.size)]
@@ -128,6 +192,14 @@ def main():
         for grid in grids:
             for layout, major in (("block", "R"), ("cyclic", "C")):
                 r = run_case(world, name, grid, layout, major)
+                results.append(r)
+                bad += len(r["fails"])
+                if world.rank == 0:
+                    print(("FAIL " if r["fails"] else "ok   ") + json.dumps(r), flush=True)
+    for name in [x for x in a.pseudo_cases.split(",") if x]:
+        for grid in grids:
+            for layout, major in (("block", "R"), ("cyclic", "C")):
+                r = run_pseudo_case(world, name, grid, layout, major)
                 results.append(r)
                 bad += len(r["fails"])
                 if world.rank == 0:
