@@ -203,3 +203,76 @@ def run(a):
     world.close()
     if tdist.is_initialized():
         tdist.destroy_process_group()
+
+
+# ---- pseudo-Hermitian (BSE) benchmark matrix (BASELINE config C5) ---------------------------------------------------
+def bse_terms(N: int, seed: int = 11, lam_min: float = 1.0, lam_max: float = 100.0, coupling: float = 0.3,
+              nrefl: int = 3):
+    """Low-rank description of the synthetic BSE matrix H = [[A, B], [-conj(B), -conj(A)]] with exactly known
+    spectrum +-lam (same matrix as the test generator oracle.chase_oracle.bse_matrix, checked in
+    tests/test_pseudo_cpu.py):  A = Q diag(a) Q^H, B = Q diag(b) Q^T, Q = I + X Y^H (nrefl Householder reflectors),
+        A = diag(a) + X Ga + Pa X^H,   Ga = Y^H diag(a) + (Y^H diag(a) Y) X^H,        Pa = diag(a) Y
+        B = diag(b) + X Gb + Pb X^T,   Gb = Y^H diag(b) + (Y^H diag(b) conj(Y)) X^T,  Pb = diag(b) conj(Y)
+    so that every rank can form its own block on its own GPU from O(N) data."""
+    assert N % 2 == 0
+    k = N // 2
+    rng = np.random.default_rng(seed)
+    lam = lam_min + (lam_max - lam_min) * (np.arange(k) / max(k - 1, 1))
+    phase = np.exp(2j * np.pi * rng.random(k))
+    b = coupling * lam * phase
+    a = np.sqrt(lam**2 + np.abs(b) ** 2)
+    X = np.zeros((k, nrefl), dtype=np.complex128)
+    Y = np.zeros((k, nrefl), dtype=np.complex128)
+    for p in range(nrefl):
+        v = rng.standard_normal(k) + 1j * rng.standard_normal(k)
+        v /= np.linalg.norm(v)
+        Qv = v + X[:, :p] @ (Y[:, :p].conj().T @ v)
+        X[:, p] = -2.0 * Qv
+        Y[:, p] = v
+    Ya = Y.conj().T * a
+    Ga = Ya + (Ya @ Y) @ X.conj().T
+    Pa = a[:, None] * Y
+    Yb = Y.conj().T * b
+    Gb = Yb + (Yb @ Y.conj()) @ X.T
+    Pb = b[:, None] * Y.conj()
+    return dict(k=k, lam=lam, a=a, b=b, X=X, Ga=Ga, Pa=Pa, Gb=Gb, Pb=Pb)
+
+
+def bse_local_block(N, gr, gc, device, dtype=None, transposed=False, terms=None):
+    """This rank's block H[gr, gc] of the synthetic BSE matrix as a torch tensor (m_loc, n_loc), or with
+    transposed=True as (n_loc, m_loc) row-major = the column-major m_loc x n_loc array the solver wants."""
+    import torch
+
+    t = terms or bse_terms(N)
+    k = t["k"]
+    dt = dtype or torch.complex128
+    gr, gc = np.asarray(gr), np.asarray(gc)
+    Hb = torch.zeros((len(gr), len(gc)), dtype=torch.complex128, device=device)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(device)  # noqa: E731
+    rsel = [np.nonzero(gr < k)[0], np.nonzero(gr >= k)[0]]
+    csel = [np.nonzero(gc < k)[0], np.nonzero(gc >= k)[0]]
+    for bi in (0, 1):
+        for bj in (0, 1):
+            ri, cj = rsel[bi], csel[bj]
+            if len(ri) == 0 or len(cj) == 0:
+                continue
+            lr, lc = gr[ri] - bi * k, gc[cj] - bj * k  # indices inside the k x k sub-block
+            if bi == bj:  # A (top-left) or -conj(A) (bottom-right)
+                blk = dev(t["X"][lr]) @ dev(t["Ga"][:, lc]) + dev(t["Pa"][lr]) @ dev(t["X"][lc].conj().T)
+                dvec = t["a"]
+            else:  # B (top-right) or -conj(B) (bottom-left)
+                blk = dev(t["X"][lr]) @ dev(t["Gb"][:, lc]) + dev(t["Pb"][lr]) @ dev(t["X"][lc].T)
+                dvec = t["b"]
+            pos = {int(g): q for q, g in enumerate(lc)}
+            rows = [q for q, g in enumerate(lr) if int(g) in pos]
+            if rows:
+                cols = [pos[int(lr[q])] for q in rows]
+                blk[rows, cols] += dev(dvec[lr[rows]].astype(np.complex128))
+            if bi == 1:
+                blk = -blk.conj()
+            Hb[torch.from_numpy(ri).to(device)[:, None], torch.from_numpy(cj).to(device)[None, :]] = blk
+            del blk
+    Hb = Hb.to(dt)
+    if transposed:
+        Hb = Hb.T.contiguous()
+    return Hb, t["lam"]

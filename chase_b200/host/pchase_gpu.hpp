@@ -599,6 +599,7 @@ public:
     void keep_device_matrix(bool f) { keep_device_matrix_ = f; }
     void use_device_rng(bool f) { device_rng_ = f; }
     std::size_t heev_sweeps() const { return heev_sweeps_; }
+    std::size_t hemm_cols() const { return hemm_cols_; } // columns actually multiplied by the filter
     std::size_t gather_passes() const { return gathers_; }
     std::size_t collectives() const { return comm_.collectives(); }
     std::size_t local_rows() const { return m_loc_; }

@@ -4,7 +4,12 @@
 
 A = Q diag(lambda) Q^H with the reference generator's uniform spectrum (lambda_k = 100 (1e-4 + k (1 - 1e-4) / N),
 examples/2_input_output/2_input_output.cpp:250-262) and Q = 3 Householder reflectors; every rank forms its
-block-cyclic block from 9 rank-one terms on its own GPU and hands it to the solver on the device."""
+block-cyclic block from 9 rank-one terms on its own GPU and hands it to the solver on the device.
+
+    torchrun --nproc-per-node 8 scripts/run_dist.py --pseudo --type z --N 40000 --nev 500 --nex 200   # config C5
+
+--pseudo: the pseudo-Hermitian (BSE) problem class through p?chase_init_pseudo_blockcyclic_ on the synthetic BSE matrix
+of chase_b200.bench_dist.bse_terms (spectrum +-lam known exactly; type z or c)."""
 import argparse
 import json
 import os
@@ -27,6 +32,9 @@ ap.add_argument("--nex", type=int, default=400)
 ap.add_argument("--nb", type=int, default=64)
 ap.add_argument("--solves", type=int, default=1)
 ap.add_argument("--out", default="")
+ap.add_argument("--pseudo", action="store_true")
+ap.add_argument("--tol", type=float, default=0.0)
+ap.add_argument("--deg", type=int, default=20)
 a = ap.parse_args()
 
 L = chase_b200.lib()
@@ -35,11 +43,16 @@ G = world.size
 r, c = cd.grid_dims(G)
 i, j = cd.grid_coords(r, c, "R", world.rank)
 gr, gc = cd.global_indices(a.N, r, a.nb, i), cd.global_indices(a.N, c, a.nb, j)
-cplx = a.type == "z"
-dt = np.complex128 if cplx else np.float64
-solver = cd.PChASE(world, a.N, a.nev, a.nex, dt, grid=(r, c), major="R", mb=a.nb, nb=a.nb)
+cplx = a.type in ("z", "c")
+dt = {"z": np.complex128, "c": np.complex64, "d": np.float64}[a.type]
+tol = a.tol or (1e-10 if a.type in ("z", "d") else 1e-5)
+solver = cd.PChASE(world, a.N, a.nev, a.nex, dt, grid=(r, c), major="R", mb=a.nb, nb=a.nb, pseudo=a.pseudo)
 # row-major (n_loc, m_loc) == column-major m_loc x n_loc with ld = m_loc
-At, lam = bd.local_block(a.N, gr, gc, cplx, f"cuda:{world.device}", transposed=True)
+if a.pseudo:
+    At, lam = bd.bse_local_block(a.N, gr, gc, f"cuda:{world.device}",
+                                 dtype=torch.complex128 if a.type == "z" else torch.complex64, transposed=True)
+else:
+    At, lam = bd.local_block(a.N, gr, gc, cplx, f"cuda:{world.device}", transposed=True)
 solver.load_device_matrix(At.data_ptr(), len(gr))
 del At
 torch.cuda.empty_cache()
@@ -52,18 +65,21 @@ for s in range(a.solves):
     world.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = solver.solve(deg=20, tol=1e-10, copy=False)
+    res = solver.solve(deg=a.deg, tol=tol, copy=False)
     e1.record()
     torch.cuda.synchronize()
     secs = world.max(e0.elapsed_time(e1) * 1e-3)
     rel = float(np.max(np.abs(res.ritzv[:a.nev] - lam[:a.nev]) / lam[:a.nev]))
     st = res.stats
-    rec = dict(type=a.type, N=a.N, nev=a.nev, nex=a.nex, gpus=G, grid=f"{r}x{c}", layout=f"block-cyclic {a.nb}",
+    es = np.dtype(dt).itemsize
+    rec = dict(type=a.type, pseudo_hermitian=bool(a.pseudo), tol=tol, N=a.N, nev=a.nev, nex=a.nex, gpus=G,
+               grid=f"{r}x{c}", layout=f"block-cyclic {a.nb}",
                time_to_solution_s=secs, iterations=res.iterations, filtered_vecs=res.filtered_vecs,
                filter_tflops_whole_job=st["gflop_filter"] / st["t_filter"] / 1e3,
                filter_tflops_per_gpu=st["gflop_filter"] / st["t_filter"] / 1e3 / G,
                phases_s={k[2:]: st[k] for k in st if k.startswith("t_")}, max_rel_eig_err=rel,
-               max_resid=float(res.resid[:a.nev].max()), local_matrix_gb=len(gr) * len(gc) * (16 if cplx else 8) / 1e9)
+               max_resid=float(res.resid[:a.nev].max()), local_matrix_gb=len(gr) * len(gc) * es / 1e9,
+               qr=res.qr_log, heev_sweeps=st["heev_sweeps"])
     out.append(rec)
     if world.rank == 0:
         print(json.dumps(rec), flush=True)

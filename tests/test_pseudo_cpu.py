@@ -137,3 +137,20 @@ def test_new_driver_is_call_identical_to_reference_driver(exe, args):
     assert out.returncode == 0, out.stderr[-2000:]
     j = json.loads(out.stdout)
     assert j["identical"] is True and j["iterations"] >= 1
+
+
+def test_benchmark_bse_block_generator_equals_oracle_matrix():
+    """chase_b200.bench_dist.bse_local_block (per-rank blocks from O(N) data, used by scripts/run_dist.py --pseudo for
+    BASELINE config C5) builds the same matrix as the dense test generator."""
+    from chase_b200 import bench_dist as bd
+
+    N = 96
+    H, lam = co.bse_matrix(N)
+    rng = np.random.default_rng(0)
+    gr = np.sort(rng.choice(N, 40, replace=False))
+    gc = np.sort(rng.choice(N, 50, replace=False))
+    blk, lam2 = bd.bse_local_block(N, gr, gc, "cpu")
+    assert np.abs(blk.numpy() - H[np.ix_(gr, gc)]).max() < 1e-12
+    assert np.array_equal(lam, lam2)
+    blkT, _ = bd.bse_local_block(N, np.arange(N), np.arange(N), "cpu", transposed=True)
+    assert np.abs(blkT.numpy().T - H).max() < 1e-12
