@@ -207,7 +207,7 @@ def run(a):
 
 # ---- pseudo-Hermitian (BSE) benchmark matrix (BASELINE config C5) ---------------------------------------------------
 def bse_terms(N: int, seed: int = 11, lam_min: float = 1.0, lam_max: float = 100.0, coupling: float = 0.3,
-              nrefl: int = 3):
+              nrefl: int = 3):  # same defaults as oracle.chase_oracle.bse_matrix
     """Low-rank description of the synthetic BSE matrix H = [[A, B], [-conj(B), -conj(A)]] with exactly known
     spectrum +-lam (same matrix as the test generator oracle.chase_oracle.bse_matrix, checked in
     tests/test_pseudo_cpu.py):  A = Q diag(a) Q^H, B = Q diag(b) Q^T, Q = I + X Y^H (nrefl Householder reflectors),
@@ -238,12 +238,12 @@ def bse_terms(N: int, seed: int = 11, lam_min: float = 1.0, lam_max: float = 100
     return dict(k=k, lam=lam, a=a, b=b, X=X, Ga=Ga, Pa=Pa, Gb=Gb, Pb=Pb)
 
 
-def bse_local_block(N, gr, gc, device, dtype=None, transposed=False, terms=None):
+def bse_local_block(N, gr, gc, device, dtype=None, transposed=False, terms=None, **kw):
     """This rank's block H[gr, gc] of the synthetic BSE matrix as a torch tensor (m_loc, n_loc), or with
     transposed=True as (n_loc, m_loc) row-major = the column-major m_loc x n_loc array the solver wants."""
     import torch
 
-    t = terms or bse_terms(N)
+    t = terms or bse_terms(N, **kw)
     k = t["k"]
     dt = dtype or torch.complex128
     gr, gc = np.asarray(gr), np.asarray(gc)
@@ -252,9 +252,13 @@ def bse_local_block(N, gr, gc, device, dtype=None, transposed=False, terms=None)
     rsel = [np.nonzero(gr < k)[0], np.nonzero(gr >= k)[0]]
     csel = [np.nonzero(gc < k)[0], np.nonzero(gc >= k)[0]]
     for bi in (0, 1):
+        ri = rsel[bi]
+        if len(ri) == 0:
+            continue
+        rowblk = torch.zeros((len(ri), len(gc)), dtype=torch.complex128, device=device)
         for bj in (0, 1):
-            ri, cj = rsel[bi], csel[bj]
-            if len(ri) == 0 or len(cj) == 0:
+            cj = csel[bj]
+            if len(cj) == 0:
                 continue
             lr, lc = gr[ri] - bi * k, gc[cj] - bj * k  # indices inside the k x k sub-block
             if bi == bj:  # A (top-left) or -conj(A) (bottom-right)
@@ -270,8 +274,10 @@ def bse_local_block(N, gr, gc, device, dtype=None, transposed=False, terms=None)
                 blk[rows, cols] += dev(dvec[lr[rows]].astype(np.complex128))
             if bi == 1:
                 blk = -blk.conj()
-            Hb[torch.from_numpy(ri).to(device)[:, None], torch.from_numpy(cj).to(device)[None, :]] = blk
+            rowblk.index_copy_(1, torch.from_numpy(cj).to(device), blk.resolve_conj())
             del blk
+        Hb.index_copy_(0, torch.from_numpy(ri).to(device), rowblk)
+        del rowblk
     Hb = Hb.to(dt)
     if transposed:
         Hb = Hb.T.contiguous()

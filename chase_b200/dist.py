@@ -165,7 +165,13 @@ class PChASE:
         return _p(self.H) if self.H is not None else ctypes.c_void_p(0)
 
     def load_device_matrix(self, dev_ptr: int, ld: int):
-        """Hand over this rank's block as a column-major device array (e.g. a torch tensor's data_ptr())."""
+        """Hand over this rank's block as a column-major device array (e.g. a torch tensor's data_ptr()).
+
+        The library copies on its own (non-blocking) stream, which does not wait for torch's streams: the producer
+        of the block is synchronised here first."""
+        import torch
+
+        torch.cuda.synchronize()
         rc = self._lib.chase_b200_dist_load_device_matrix_(ctypes.c_char_p(self.pfx.encode()), ctypes.c_void_p(dev_ptr),
                                                            ctypes.byref(ctypes.c_longlong(ld)))
         if rc != 0:
@@ -191,7 +197,14 @@ class PChASE:
         st = np.zeros(16)
         L.chase_b200_get_stats_(_p(st), _i(16))
         if st[15] != 0:
-            raise RuntimeError("chase_b200: distributed solve failed")
+            msg = "chase_b200: distributed solve failed"
+            if trace:  # the call trace up to the failure is the best diagnostic there is
+                n = L.chase_b200_trace_copy_(None, 0)
+                buf = ctypes.create_string_buffer(n + 1)
+                L.chase_b200_trace_copy_(buf, n + 1)
+                tail = [t[:160] for t in buf.value.decode().splitlines()][-25:]
+                msg += "; last calls:\n  " + "\n  ".join(tail)
+            raise RuntimeError(msg)
         res = SolveResult(self.ritzv.copy(), resid, self.V.copy(order="F") if copy else self.V,
                           dict(zip(STAT_NAMES, st.tolist())))
         if trace:

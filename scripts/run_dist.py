@@ -35,6 +35,10 @@ ap.add_argument("--out", default="")
 ap.add_argument("--pseudo", action="store_true")
 ap.add_argument("--tol", type=float, default=0.0)
 ap.add_argument("--deg", type=int, default=20)
+ap.add_argument("--lam-max", type=float, default=100.0, help="--pseudo: positive spectrum is uniform in [1, lam-max]")
+ap.add_argument("--upperb-scale", type=float, default=1.0,
+                help="chase_set_upperb_scale_rate_: safety factor on the Lanczos estimate of max(lambda^2)")
+ap.add_argument("--max-iter", type=int, default=25)
 a = ap.parse_args()
 
 L = chase_b200.lib()
@@ -50,7 +54,8 @@ solver = cd.PChASE(world, a.N, a.nev, a.nex, dt, grid=(r, c), major="R", mb=a.nb
 # row-major (n_loc, m_loc) == column-major m_loc x n_loc with ld = m_loc
 if a.pseudo:
     At, lam = bd.bse_local_block(a.N, gr, gc, f"cuda:{world.device}",
-                                 dtype=torch.complex128 if a.type == "z" else torch.complex64, transposed=True)
+                                 dtype=torch.complex128 if a.type == "z" else torch.complex64, transposed=True,
+                                 lam_max=a.lam_max)
 else:
     At, lam = bd.local_block(a.N, gr, gc, cplx, f"cuda:{world.device}", transposed=True)
 solver.load_device_matrix(At.data_ptr(), len(gr))
@@ -59,20 +64,23 @@ torch.cuda.empty_cache()
 import ctypes  # noqa: E402
 
 L.chase_b200_set_device_rng_(ctypes.byref(ctypes.c_int(1)))
+L.chase_set_upperb_scale_rate_(ctypes.byref(ctypes.c_float(a.upperb_scale)))
+L.chase_set_max_iter_(ctypes.byref(ctypes.c_int(a.max_iter)))
 out = []
 for s in range(a.solves):
     torch.cuda.synchronize()
     world.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = solver.solve(deg=a.deg, tol=tol, copy=False)
+    res = solver.solve(deg=a.deg, tol=tol, copy=False, trace=bool(os.environ.get("CHASE_B200_TRACE")))
     e1.record()
     torch.cuda.synchronize()
     secs = world.max(e0.elapsed_time(e1) * 1e-3)
     rel = float(np.max(np.abs(res.ritzv[:a.nev] - lam[:a.nev]) / lam[:a.nev]))
     st = res.stats
     es = np.dtype(dt).itemsize
-    rec = dict(type=a.type, pseudo_hermitian=bool(a.pseudo), tol=tol, N=a.N, nev=a.nev, nex=a.nex, gpus=G,
+    rec = dict(type=a.type, pseudo_hermitian=bool(a.pseudo), tol=tol, lam_max=a.lam_max if a.pseudo else None,
+               upperb_scale=a.upperb_scale, N=a.N, nev=a.nev, nex=a.nex, gpus=G,
                grid=f"{r}x{c}", layout=f"block-cyclic {a.nb}",
                time_to_solution_s=secs, iterations=res.iterations, filtered_vecs=res.filtered_vecs,
                filter_tflops_whole_job=st["gflop_filter"] / st["t_filter"] / 1e3,
