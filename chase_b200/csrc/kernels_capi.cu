@@ -5,6 +5,7 @@
 #include "factor.cuh"
 #include "gemm_generic.cuh"
 #include "hemm_tma.cuh"
+#include "householder.cuh"
 #include "jacobi.cuh"
 #include "osj.cuh"
 
@@ -234,6 +235,116 @@ int trsm_impl(int64_t rows, int64_t n, const void* Rv, int64_t ldr, void* Vv, in
         // X_b = V_b inv(R_bb)
         int rc = gemm_impl<T>(0, 0, rows, nb, nb, 1.0, 0.0, V + j0 * ldv, ldv, Rinv + b * TRSM_NB * TRSM_NB, TRSM_NB, 0.0,
                               0.0, X + j0 * ldx, ldx, 0, nullptr, 0, stream);
+        if (rc)
+            return rc;
+    }
+    return 0;
+}
+
+inline dim3 grid2d(int64_t rows, int64_t cols);
+
+// Householder QR of the rows x n matrix A (rows >= n): on exit Q holds the orthonormal factor (LAPACK ?geqrf +
+// ?orgqr/?ungqr conventions), A holds R in its upper triangle and the reflectors below.  Workspace layout (elements of
+// T unless noted): Vp rows x NB | W NB x n | W2 NB x n | Tall NB x n | G NB x NB | tau n (compute type) | split-K
+// scratch for the deep, narrow V^H C products.
+constexpr size_t HH_SPLITK_BYTES = size_t(32) << 20;
+inline size_t hhqr_ws_bytes(int64_t rows, int64_t n, int elem_bytes)
+{
+    const size_t nb = HH_NB;
+    return ((size_t)rows * nb + 3 * nb * (size_t)n + nb * nb) * (size_t)elem_bytes + (size_t)n * 16 + 512 +
+           HH_SPLITK_BYTES;
+}
+
+template <class T>
+int hhqr_impl(int64_t rows, int64_t n, void* Av, int64_t lda, void* Qv, int64_t ldq, void* ws, size_t ws_bytes,
+              void* stream)
+{
+    using C_ = typename Traits<T>::comp;
+    if (n <= 0 || rows <= 0)
+        return 0;
+    if (rows < n)
+        return -2;
+    if (ws_bytes < hhqr_ws_bytes(rows, n, (int)sizeof(T)))
+        return -3;
+    cudaStream_t st = S(stream);
+    T* A = (T*)Av;
+    T* Q = (T*)Qv;
+    const int64_t NB = HH_NB;
+    T* Vp = (T*)ws;
+    T* W = Vp + (size_t)rows * NB;
+    T* W2 = W + (size_t)NB * n;
+    T* Tall = W2 + (size_t)NB * n;
+    T* G = Tall + (size_t)NB * n;
+    C_* tau = (C_*)(((uintptr_t)(G + NB * NB) + 63) & ~(uintptr_t)63);
+    void* sk = (void*)(((uintptr_t)(tau + n) + 255) & ~(uintptr_t)255);
+    auto panel_v = [&](int64_t j0, int nb) -> int
+    {
+        hh_copy_v_kernel<T><<<grid2d(rows - j0, nb), 256, 0, kcount(st)>>>(rows, j0, nb, A, lda, Vp, rows);
+        CB2_CUDA_OK(cudaGetLastError());
+        return 0;
+    };
+    // ---- factorisation ---------------------------------------------------------------------------------------
+    for (int64_t j0 = 0; j0 < n; j0 += NB)
+    {
+        const int nb = (int)std::min<int64_t>(NB, n - j0);
+        for (int64_t j = j0; j < j0 + nb; ++j)
+        {
+            hh_reflector_kernel<T><<<1, 1024, 0, kcount(st)>>>(rows, j, A, lda, tau);
+            if (j + 1 < j0 + nb)
+                hh_apply_kernel<T><<<(unsigned)(j0 + nb - j - 1), 1024, 0, kcount(st)>>>(rows, j, A, lda, tau);
+        }
+        CB2_CUDA_OK(cudaGetLastError());
+        int rc = panel_v(j0, nb);
+        if (rc)
+            return rc;
+        const int64_t len = rows - j0;
+        // T factor of the panel
+        rc = gemm_impl<T>(1, 0, nb, nb, len, 1.0, 0.0, Vp, rows, Vp, rows, 0.0, 0.0, G, NB, 0, sk, HH_SPLITK_BYTES,
+                          stream);
+        if (rc)
+            return rc;
+        T* Tp = Tall + (size_t)j0 * NB;
+        hh_larft_kernel<T><<<1, 64, 0, kcount(st)>>>(nb, G, NB, tau + j0, Tp, NB);
+        CB2_CUDA_OK(cudaGetLastError());
+        const int64_t rest = n - j0 - nb;
+        if (rest > 0)
+        {
+            // C <- (I - V T^H V^H) C,  C = A[j0:, j0+nb:]
+            T* Cm = A + j0 + (j0 + nb) * lda;
+            rc = gemm_impl<T>(1, 0, nb, rest, len, 1.0, 0.0, Vp, rows, Cm, lda, 0.0, 0.0, W, NB, 0, sk, HH_SPLITK_BYTES,
+                              stream);
+            if (rc)
+                return rc;
+            rc = gemm_impl<T>(1, 0, nb, rest, nb, 1.0, 0.0, Tp, NB, W, NB, 0.0, 0.0, W2, NB, 0, nullptr, 0, stream);
+            if (rc)
+                return rc;
+            rc = gemm_impl<T>(0, 0, len, rest, nb, -1.0, 0.0, Vp, rows, W2, NB, 1.0, 0.0, Cm, lda, 0, nullptr, 0, stream);
+            if (rc)
+                return rc;
+        }
+    }
+    // ---- Q = H_1 ... H_n [I; 0], panels applied last to first ----------------------------------------------------
+    hh_eye_kernel<T><<<grid2d(rows, n), 256, 0, kcount(st)>>>(rows, n, Q, ldq);
+    CB2_CUDA_OK(cudaGetLastError());
+    const int64_t npan = (n + NB - 1) / NB;
+    for (int64_t p = npan - 1; p >= 0; --p)
+    {
+        const int64_t j0 = p * NB;
+        const int nb = (int)std::min<int64_t>(NB, n - j0);
+        int rc = panel_v(j0, nb);
+        if (rc)
+            return rc;
+        const int64_t len = rows - j0, cols = n - j0;
+        T* Tp = Tall + (size_t)j0 * NB;
+        T* Qm = Q + j0 + j0 * ldq;
+        rc = gemm_impl<T>(1, 0, nb, cols, len, 1.0, 0.0, Vp, rows, Qm, ldq, 0.0, 0.0, W, NB, 0, sk, HH_SPLITK_BYTES,
+                          stream);
+        if (rc)
+            return rc;
+        rc = gemm_impl<T>(0, 0, nb, cols, nb, 1.0, 0.0, Tp, NB, W, NB, 0.0, 0.0, W2, NB, 0, nullptr, 0, stream);
+        if (rc)
+            return rc;
+        rc = gemm_impl<T>(0, 0, len, cols, nb, -1.0, 0.0, Vp, rows, W2, NB, 1.0, 0.0, Qm, ldq, 0, nullptr, 0, stream);
         if (rc)
             return rc;
     }
@@ -674,6 +785,11 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
+    extern "C" int chase_b200_hhqr_##X(int64_t rows, int64_t n, void* A, int64_t lda, void* Q, int64_t ldq, void* ws, \
+                                       size_t wsb, void* st)                                                          \
+    {                                                                                                                  \
+        return hhqr_impl<TT>(rows, n, A, lda, Q, ldq, ws, wsb, st);                                                   \
+    }                                                                                                                  \
     extern "C" int chase_b200_scale_rows_##X(int64_t nrows, int64_t cols, void* Xm, int64_t ldx, double a, void* st)  \
     {                                                                                                                  \
         if (nrows <= 0 || cols <= 0)                                                                                   \
@@ -741,6 +857,11 @@ extern "C" int chase_b200_tridiag_eig(int n, int batch, const double* d, const d
     jacobi_small_tridiag_kernel<<<batch, 256, 0, kcount(S(st))>>>(n, d, e, ldde, w, Z, nullptr);
     CB2_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" size_t chase_b200_hhqr_ws_bytes(int64_t rows, int64_t n, int elem_bytes)
+{
+    return hhqr_ws_bytes(rows, n, elem_bytes);
 }
 
 extern "C" size_t chase_b200_trsm_ws_bytes(int64_t n, int elem_bytes)

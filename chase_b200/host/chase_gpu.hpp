@@ -317,10 +317,10 @@ public:
         int info = 1;
         if (disable == 1 && cond != R(1.0))
         {
-            // The reference switches to Householder QR here.  Until the Householder
-            // kernel lands this backend uses its most robust Cholesky variant.
-            info = shifted_cholqr2(1.0);
-            last_qr_ = "shifted2(no-cholqr requested)";
+            // qr == 'H' / CHASE_DISABLE_CHOLQR=1: Householder QR (chase_gpu.hpp:836-857)
+            householder();
+            info = 0;
+            last_qr_ = "householder";
         }
         else if (cond > thr_upper)
         {
@@ -341,15 +341,10 @@ public:
         }
         if (info != 0)
         {
-            // reference: Householder fallback (chase_gpu.hpp:889-919).  Here: shifted
-            // CholQR with a growing shift, then fail loudly.
-            double boost = 1.0;
-            for (int attempt = 0; attempt < 4 && info != 0; ++attempt, boost *= 100.0)
-                info = shifted_cholqr2(boost);
-            last_qr_ += "+shifted-fallback";
-            if (info != 0)
-                throw std::runtime_error("chase_b200: CholQR failed (potrf info=" + std::to_string(info) +
-                                         ") and no Householder fallback is available yet");
+            // CholeskyQR broke down (potrf info != 0): Householder QR, as the reference (chase_gpu.hpp:889-919).
+            // A failed round may already have replaced V1 by a partly orthogonalised block spanning the same space.
+            householder();
+            last_qr_ += "+householder";
         }
         qr_log_.push_back(last_qr_);
         if (kPseudo)
@@ -664,6 +659,19 @@ private:
         std::swap(dV1_, dW_);
         return 0;
     }
+    // V1 <- orthonormal factor of V1 (all nc_ columns) by Householder reflections
+    void householder()
+    {
+        const std::size_t need = chase_b200_hhqr_ws_bytes((int64_t)N_, (int64_t)nc_, (int)sizeof(T));
+        if (hh_ws_bytes_ < need)
+        {
+            hh_ws_ = alloc<unsigned char>(need);
+            hh_ws_bytes_ = need;
+        }
+        CB2_KCHECK(KK::hhqr((int64_t)N_, (int64_t)nc_, dV1_, (int64_t)ld_, dW_, (int64_t)ld_, hh_ws_, hh_ws_bytes_,
+                            stream_));
+        std::swap(dV1_, dW_);
+    }
     int shifted_cholqr2(double boost)
     {
         int info = chol_round(true, boost);
@@ -881,8 +889,8 @@ private:
     T *dM_ = nullptr, *dRinv_ = nullptr, *dT_ = nullptr; // pseudo-Hermitian RR only
     double* ones_ = nullptr;
     T* dV0_ = nullptr; // device copy of the reference start block (parity mode), filled at the first random solve
-    unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr;
-    std::size_t heev_ws_bytes_ = 0, trsm_ws_bytes_ = 0, splitk_ws_bytes_ = 0;
+    unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr, *hh_ws_ = nullptr;
+    std::size_t heev_ws_bytes_ = 0, trsm_ws_bytes_ = 0, splitk_ws_bytes_ = 0, hh_ws_bytes_ = 0;
     double *dTheta_ = nullptr, *dNorms_ = nullptr;
     int *dInfo_ = nullptr, *dIdx_ = nullptr;
     T* lan_v_ = nullptr;

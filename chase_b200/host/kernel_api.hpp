@@ -39,6 +39,7 @@ struct K;
         static constexpr auto herm_check = chase_b200_herm_check_##X;                                                  \
         static constexpr auto shift_diag = chase_b200_shift_diag_##X;                                                  \
         static constexpr auto herm_mirror = chase_b200_herm_mirror_##X;                                                \
+        static constexpr auto hhqr = chase_b200_hhqr_##X;                                                              \
         static constexpr auto scale_rows = chase_b200_scale_rows_##X;                                                  \
         static constexpr auto scale_rows_map = chase_b200_scale_rows_map_##X;                                          \
         static constexpr auto kconj = chase_b200_kconj_##X;                                                            \

@@ -290,8 +290,9 @@ public:
         int info = 1;
         if (disable == 1 && cond != R(1.0))
         {
-            info = shifted_cholqr2(1.0);
-            last_qr_ = "shifted2(no-cholqr requested)";
+            householder(); // qr == 'H' / CHASE_DISABLE_CHOLQR=1 (pchase_gpu.hpp:1142-1190)
+            info = 0;
+            last_qr_ = "householder";
         }
         else if (cond > thr_upper)
         {
@@ -312,13 +313,8 @@ public:
         }
         if (info != 0)
         {
-            double boost = 1.0;
-            for (int attempt = 0; attempt < 4 && info != 0; ++attempt, boost *= 100.0)
-                info = shifted_cholqr2(boost);
-            last_qr_ += "+shifted-fallback";
-            if (info != 0)
-                throw std::runtime_error("chase_b200: CholQR failed (potrf info=" + std::to_string(info) +
-                                         ") and no Householder fallback is available yet");
+            householder(); // CholeskyQR broke down: Householder QR, as the reference (pchase_gpu.hpp:1254-1300)
+            last_qr_ += "+householder";
         }
         qr_log_.push_back(last_qr_);
         if (kPseudo)
@@ -791,6 +787,24 @@ private:
         std::swap(dV1_, dVs_);
         return 0;
     }
+    // Householder fallback.  The reference runs a distributed panel factorisation (nccl/householder_qr.hpp, 3000
+    // lines of scalar allreduces per column); the fallback is rare and the whole N x nc panel fits on one GPU
+    // (C4: 2.7 GB), so here the column-layout pieces are all-gathered inside the grid column, every GPU factorises the
+    // full-length copy with the single-GPU kernel (identical inputs -> identical results) and keeps its own rows.
+    void householder()
+    {
+        if (hh_a_ == nullptr)
+        {
+            hh_a_ = alloc<T>(ldn_ * nc_);
+            hh_q_ = alloc<T>(ldn_ * nc_);
+            hh_ws_bytes_ = chase_b200_hhqr_ws_bytes((int64_t)N_, (int64_t)nc_, (int)sizeof(T));
+            hh_ws_ = alloc<unsigned char>(hh_ws_bytes_);
+        }
+        v_to_full(dV1_, hh_a_, nc_);
+        CB2_KCHECK(KK::hhqr((int64_t)N_, (int64_t)nc_, hh_a_, (int64_t)ldn_, hh_q_, (int64_t)ldn_, hh_ws_, hh_ws_bytes_,
+                            stream_));
+        full_to_v(hh_q_, dV1_, nc_);
+    }
     int shifted_cholqr2(double boost)
     {
         int info = chol_round(true, boost);
@@ -1054,8 +1068,9 @@ private:
     T *dM_ = nullptr, *dRinv_ = nullptr, *dT_ = nullptr, *dFull_ = nullptr; // pseudo-Hermitian only
     double* ones_ = nullptr;
     T* dV0_ = nullptr; // device copy of this rank's rows of the reference start block (parity mode)
-    unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr;
-    std::size_t heev_ws_bytes_ = 0, trsm_ws_bytes_ = 0, splitk_ws_bytes_ = 0;
+    unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr, *hh_ws_ = nullptr;
+    std::size_t heev_ws_bytes_ = 0, trsm_ws_bytes_ = 0, splitk_ws_bytes_ = 0, hh_ws_bytes_ = 0;
+    T *hh_a_ = nullptr, *hh_q_ = nullptr; // full-length copies for the Householder fallback (allocated on first use)
     double *dTheta_ = nullptr, *dNorms_ = nullptr;
     int *dInfo_ = nullptr, *dIdx_ = nullptr;
     int64_t *map_v2w_ = nullptr, *map_v2full_ = nullptr, *map_w2full_ = nullptr, *map_full2v_ = nullptr,

@@ -217,3 +217,17 @@ def lanczos_pseudo_step(rows, nv, k, M, v0, v1, v2, ld, d, bnorm):
     f = getattr(lib(), f"chase_b200_lanczos_pseudo_step_{_sfx(v1)}")
     return _chk(f(ctypes.c_int64(rows), int(nv), int(k), int(M), _ptr(v0), _ptr(v1), _ptr(v2), ctypes.c_int64(ld),
                   _ptr(d), _ptr(bnorm), _stream()), "lanczos_pseudo_step")
+
+
+def hhqr(rows, n, A, lda, Q, ldq):
+    """Householder QR: Q <- orthonormal factor of A (rows x n), A <- R and the reflectors."""
+    import torch
+
+    L = lib()
+    L.chase_b200_hhqr_ws_bytes.restype = ctypes.c_size_t
+    L.chase_b200_hhqr_ws_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+    nbytes = L.chase_b200_hhqr_ws_bytes(rows, n, A.element_size())
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=A.device)
+    f = getattr(L, f"chase_b200_hhqr_{_sfx(A)}")
+    return _chk(f(ctypes.c_int64(rows), ctypes.c_int64(n), _ptr(A), ctypes.c_int64(lda), _ptr(Q), ctypes.c_int64(ldq),
+                  _ptr(ws), ctypes.c_size_t(nbytes), _stream()), "hhqr")

@@ -118,6 +118,13 @@ extern "C"
     int chase_b200_shift_diag_##X(int64_t n, void* A, int64_t lda, double c, void* stream);                           \
     /* Mirror one triangle onto the other (symOrHermMatrix, reference chase_gpu.hpp:472-505). */                      \
     int chase_b200_herm_mirror_##X(int64_t n, void* A, int64_t lda, int from_upper, void* stream);                    \
+    /* Householder QR of the rows x n matrix A (rows >= n): Q <- orthonormal factor (LAPACK ?geqrf + ?orgqr/?ungqr       \
+       conventions: R_jj real, sign -sign(Re x_j)), A <- R (upper triangle) and the reflectors.  ws: at least            \
+       chase_b200_hhqr_ws_bytes(rows, n, sizeof(element)).  Replaces cusolverDnTgeqrf + cusolverDnTorgqr/ungqr of        \
+       cuda::houseHoulderQR (reference linalg/internal/cuda/cholqr.hpp:524-556), the fallback of ChASEGPU::QR when       \
+       CholQR breaks down or qr == 'H' (Impl/chase_gpu/chase_gpu.hpp:836-919). */                                        \
+    int chase_b200_hhqr_##X(int64_t rows, int64_t n, void* A, int64_t lda, void* Q, int64_t ldq, void* ws,            \
+                            size_t ws_bytes, void* stream);                                                           \
     /* X[0:nrows, 0:cols] *= a (X points at the first row to scale).  a = -1 on rows [N/2, N) is S X of the           \
        pseudo-Hermitian path (reference cuda/flipSign.cu, chase_gpu.hpp:752-782); a = 1e-3 is the start-vector        \
        damping of the lower block (chase_gpu.hpp:518-529). */                                                         \
@@ -152,6 +159,7 @@ extern "C"
                                double* Z_dev, void* stream);
 
     size_t chase_b200_trsm_ws_bytes(int64_t n, int elem_bytes);
+    size_t chase_b200_hhqr_ws_bytes(int64_t rows, int64_t n, int elem_bytes);
     size_t chase_b200_heev_ws_bytes(int64_t n, int is_complex);
     /* Which HEMM implementation handles this shape: 0 = generic DMMA tiles, 1 = TMA-fed DMMA pipeline. */
     int chase_b200_hemm_path(int dtype_code, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc);

@@ -36,8 +36,15 @@ def run_case(world, name, grid, layout, major):
     i, j = cd.grid_coords(r, c, major, world.rank)
     gr, gc = cd.global_indices(N, r, nb, i), cd.global_indices(N, c, nb, j)
     Hloc = np.asfortranarray(H[np.ix_(gr, gc)])
-    with cd.PChASE(world, N, nev, nex, Hloc, grid=grid, major=major, mb=nb, nb=nb) as s:
-        res = s.solve(deg=g["deg"], tol=g["tol"], opt="S" if g["opt"] else "N", trace=True)
+    os.environ.update(g.get("env", {}))  # e.g. CHASE_DISABLE_CHOLQR=1: Householder QR in every iteration
+    try:
+        with cd.PChASE(world, N, nev, nex, Hloc, grid=grid, major=major, mb=nb, nb=nb) as s:
+            res = s.solve(deg=g["deg"], tol=g["tol"], opt="S" if g["opt"] else "N", trace=True)
+    finally:
+        for k in g.get("env", {}):
+            os.environ.pop(k, None)
+    if g.get("env", {}).get("CHASE_DISABLE_CHOLQR") == "1" and "householder" not in res.qr_log:
+        return dict(case=name, grid=f"{grid[0]}x{grid[1]}", layout=layout, major=major, fails=["Householder QR not used"])
     ref, got = parse_trace(p["trace"]), parse_trace(res.trace)
     fails = []
     if res.iterations != p["iterations"]:
@@ -177,7 +184,8 @@ def run_sequence(world, name, grid, layout, major):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", default="serial_clement_d_N256,serial_clement_z_N256,c1_clement_d_N1001,c2s_uniform_d_N2000")
+    ap.add_argument("--cases", default="serial_clement_d_N256,serial_clement_z_N256,c1_clement_d_N1001,c2s_uniform_d_N2000,"
+                                       "hhqr_clement_z_N256")
     ap.add_argument("--grid", default="")
     ap.add_argument("--out", default="")
     ap.add_argument("--no-seq", action="store_true")

@@ -33,6 +33,11 @@ CASES = {
     "seq_clement_d_N400": dict(type="d", N=400, nev=40, nex=20, matrix="clement", tol=1e-10, deg=20, seq=3, perturb=1e-4),
     # no degree optimisation
     "noopt_clement_d_N300": dict(type="d", N=300, nev=30, nex=10, matrix="clement", tol=1e-10, deg=20, opt=0),
+    # Householder QR in every iteration (reference: CHASE_DISABLE_CHOLQR=1 -> houseHoulderQR, chase_cpu.hpp:670-690)
+    "hhqr_clement_d_N300": dict(type="d", N=300, nev=30, nex=10, matrix="clement", tol=1e-10, deg=20,
+                                env={"CHASE_DISABLE_CHOLQR": "1"}),
+    "hhqr_clement_z_N256": dict(type="z", N=256, nev=24, nex=16, matrix="clement", tol=1e-10, deg=16,
+                                env={"CHASE_DISABLE_CHOLQR": "1"}),
     # pseudo-Hermitian (BSE) solves, reference binary chase_ref_cpu_p<z|c> (Solve_pseudo).  First case = the
     # configuration of /root/reference/tests/chase_distributed_solve_pseudo_bse_test.cpp:131-250 on the reference's
     # own fixture; "bse_fixture:<file>" is read from tests/golden/bse_fixtures/, "bse_synth:<seed>" is
@@ -55,7 +60,7 @@ def run_case(name, c):
     cmd = [exe, "--out", out]
     tmp = None
     for k, v in c.items():
-        if k == "type":
+        if k in ("type", "env"):
             continue
         if k == "matrix" and str(v).startswith("bse_fixture:"):
             v = "file:" + os.path.join(HERE, "bse_fixtures", v.split(":", 1)[1])
@@ -70,10 +75,12 @@ def run_case(name, c):
             Hm.T.tofile(tmp)  # column-major on disk
             v = "file:" + tmp
         cmd += [f"--{k}", str(v)]
-    env = dict(os.environ, OPENBLAS_NUM_THREADS="8", OMP_NUM_THREADS="8")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="8", OMP_NUM_THREADS="8", **c.get("env", {}))
     subprocess.check_call(cmd, env=env, stdout=subprocess.DEVNULL)
     j = json.load(open(out))
     j["matrix"] = c["matrix"]
+    if "env" in c:
+        j["env"] = c["env"]
     if tmp:
         os.remove(tmp)
     # keep fixtures small: round-trip through json with no extra whitespace
