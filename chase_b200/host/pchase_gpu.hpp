@@ -36,6 +36,8 @@
 
 #include <cuda_runtime_api.h>
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -110,14 +112,24 @@ public:
         trsm_ws_ = alloc<unsigned char>(trsm_ws_bytes_);
         splitk_ws_bytes_ = std::max<std::size_t>(std::size_t(64) << 20, 4 * nc_ * nc_ * 16);
         splitk_ws_ = alloc<unsigned char>(splitk_ws_bytes_);
-        dTheta_ = alloc<double>(nc_);
-        dNorms_ = alloc<double>(nc_);
+        dTheta_ = alloc<double>(std::max<std::size_t>(nc_, 64)); // >= communicator size (warm-up all-gather)
+        dNorms_ = alloc<double>(std::max<std::size_t>(nc_, 64));
         dInfo_ = alloc<int>(4);
         dIdx_ = alloc<int>(2 * nc_);
         resid_.assign(nc_, R(0));
         perm_.resize(nc_);
         reset_perm();
         build_maps();
+        // NCCL connects a communicator's peers lazily inside its first collective (0.1-0.3 s): do that here, like
+        // the rest of the set-up, instead of inside the first QR of the first solve
+        comm_.allreduce_sum(dNorms_, 1, comm_.world(), stream_);
+        comm_.allreduce_sum(dNorms_, 1, comm_.row(), stream_);
+        comm_.allreduce_sum(dNorms_, 1, comm_.col(), stream_);
+        comm_.allgather(dNorms_, dTheta_, 1, comm_.row(), stream_);
+        comm_.allgather(dNorms_, dTheta_, 1, comm_.col(), stream_);
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        CB2_CHECK(cudaMemsetAsync(dNorms_, 0, nc_ * sizeof(double), stream_));
+        CB2_CHECK(cudaMemsetAsync(dTheta_, 0, nc_ * sizeof(double), stream_));
         const char* e = std::getenv("CHASE_B200_DEVICE_RNG");
         device_rng_ = e && std::atoi(e) != 0;
     }
@@ -559,6 +571,10 @@ public:
     void End() override
     {
         flush_perm();
+        if (qrt_.on && grid_.rank == 0)
+            std::fprintf(stderr, "chase_b200 QR timing: %d rounds, gram %.3f s (max %.4f), allreduce+bcast %.3f s (max "
+                                 "%.4f), potrf %.3f s (max %.4f), trsm %.3f s (max %.4f)\n", qrt_.rounds, qrt_.t[0],
+                         qrt_.tmax[0], qrt_.t[1], qrt_.tmax[1], qrt_.t[2], qrt_.tmax[2], qrt_.t[3], qrt_.tmax[3]);
         if (m_loc_ > 0)
             CB2_CHECK(cudaMemcpy2DAsync(V_, ldvh_ * sizeof(T), dV1_, ldv_ * sizeof(T), m_loc_ * sizeof(T), nc_,
                                         cudaMemcpyDeviceToHost, stream_));
@@ -760,15 +776,45 @@ private:
 
     // one CholQR round on all nev+nex columns (nccl/cholqr.hpp:59-256): local Gram, allreduce inside the grid
     // column, replicated Cholesky, local TRSM
+    // CHASE_B200_QR_TIMING=1: wall-clock split of the CholQR rounds (synchronises after every step; diagnostics only)
+    struct QrTimer
+    {
+        bool on = std::getenv("CHASE_B200_QR_TIMING") != nullptr;
+        double t[5] = {0, 0, 0, 0, 0}, tmax[5] = {0, 0, 0, 0, 0};
+        int rounds = 0;
+        std::chrono::high_resolution_clock::time_point t0;
+        void start(cudaStream_t s)
+        {
+            if (!on)
+                return;
+            cudaStreamSynchronize(s);
+            t0 = std::chrono::high_resolution_clock::now();
+        }
+        void lap(cudaStream_t s, int slot)
+        {
+            if (!on)
+                return;
+            cudaStreamSynchronize(s);
+            const auto t1 = std::chrono::high_resolution_clock::now();
+            const double dt = std::chrono::duration<double>(t1 - t0).count();
+            t[slot] += dt;
+            tmax[slot] = std::max(tmax[slot], dt);
+            t0 = t1;
+        }
+    } qrt_;
+
     int chol_round(bool shifted, double shift_boost)
     {
         const int64_t n = (int64_t)nc_;
+        qrt_.start(stream_);
         CB2_KCHECK(KK::gemm(1, 0, n, n, (int64_t)m_loc_, 1.0, 0.0, dV1_, (int64_t)ldv_, dV1_, (int64_t)ldv_, 0.0, 0.0,
                             dG_, (int64_t)ldg_, 1, splitk_ws_, splitk_ws_bytes_, stream_));
+        qrt_.lap(stream_, 0);
         if (grid_.r > 1)
             comm_.allreduce_sum(dG_, ldg_ * nc_, comm_.col(), stream_);
         if (grid_.c > 1)
             comm_.broadcast(dG_, ldg_ * nc_, 0, comm_.row(), stream_);
+        qrt_.lap(stream_, 1);
         if (shifted)
         {
             const double scale = (sizeof(R) == 8) ? std::sqrt((double)N_) * 2.220446049250313e-16
@@ -780,11 +826,14 @@ private:
         int info = 0;
         CB2_CHECK(cudaMemcpyAsync(&info, dInfo_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
         CB2_CHECK(cudaStreamSynchronize(stream_));
+        qrt_.lap(stream_, 2);
         if (info != 0)
             return info;
         CB2_KCHECK(KK::trsm((int64_t)m_loc_, n, dG_, (int64_t)ldg_, dV1_, (int64_t)ldv_, dVs_, (int64_t)ldv_, trsm_ws_,
                             trsm_ws_bytes_, stream_));
         std::swap(dV1_, dVs_);
+        qrt_.lap(stream_, 3);
+        qrt_.rounds++;
         return 0;
     }
     // Householder fallback.  The reference runs a distributed panel factorisation (nccl/householder_qr.hpp, 3000
