@@ -16,6 +16,9 @@ algorithm/performance.hpp:248-260) divided by time-to-solution, in TFLOP/s; `ms_
              tensor (DMMA) peak measured live on this GPU (MEASURED_PEAKS.json has no FP64 figure).
   * cpu_baseline / --impl reference: the UNMODIFIED reference CPU solver (oracle/_ref, ChASECPU + OpenBLAS) on all
              host cores on a bounded, scaled-down sample of the same workload (same generator, same nev/N, nex/nev).
+  * gpu_reference (extra key, informational): the reference's OWN single-GPU backend (ChASEGPU: cuBLAS / cuSOLVER /
+             cuRAND, oracle/_ref/chase_ref_gpu_<t>, `make -C oracle refgpu`) solving the FULL workload on this same
+             GPU from host buffers — the like-for-like comparison for `e2e` (SURVEY.md 8c/8d "same-box").
 """
 import argparse
 import ctypes
@@ -47,6 +50,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--ref-n", type=int, default=0, help="override the bounded-sample N of the CPU reference arm")
     ap.add_argument("--profile", action="store_true",
                     help="one warm solve + one profiled solve only (for `ncu`: no e2e, no CPU baseline)")
@@ -139,6 +143,35 @@ def run_reference_cpu(workload, override=0):
             "t_filter": r["timings"]["Filter"], "gflop_filter": r["gflop_filter"], "iterations": r["iterations"],
             "filtered_vecs": r["filtered_vecs"], "wall_incl_matrix_gen": wall,
             "tflops_per_solve": r["gflop_filter"] / t_all / 1e3, "tflops_filter_phase": r["gflop_filter"] / r["timings"]["Filter"] / 1e3}
+
+
+def run_reference_gpu(workload):
+    """One full-size solve with the reference's own single-GPU backend (separate process, same GPU) -> dict."""
+    t, N, nev, nex = WORKLOADS[workload]
+    exe = os.path.join(ROOT, "oracle", "_ref", f"chase_ref_gpu_{t}")
+    if not os.path.exists(exe):
+        return {"unavailable": f"{exe} not built (make -C oracle refgpu needs /root/reference)"}
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = OB + ":/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
+    env["OPENBLAS_NUM_THREADS"] = env["OMP_NUM_THREADS"] = str(min(os.cpu_count() or 1, 128))
+    out = f"/tmp/chase_refgpu_{os.getpid()}.json"
+    try:
+        subprocess.run([exe, "--N", str(N), "--nev", str(nev), "--nex", str(nex), "--matrix", "uniform_dense", "--out",
+                        out], env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900)
+        r = json.load(open(out))["problems"][0]
+        os.unlink(out)
+    except Exception as e:  # noqa: BLE001
+        err = getattr(e, "stderr", b"") or b""
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]} {err[-300:].decode(errors='replace')}"}
+    tm = r["timings"]
+    return {"impl": "reference ChASEGPU (cuBLAS / cuSOLVER / cuRAND), unmodified, same GPU, host buffers",
+            "workload": f"{t} N={N} nev={nev} nex={nex} uniform spectrum, dense (driver's own reflectors)",
+            "time_to_solution_s": tm["All"], "iterations": r["iterations"], "filtered_vecs": r["filtered_vecs"],
+            "value": r["gflop_filter"] / tm["All"] / 1e3, "unit": "TFLOP/s",
+            "filter_phase_tflops": r["gflop_filter"] / tm["Filter"] / 1e3,
+            "phases_s": {k.lower(): tm[k] for k in ("InitVecs", "Lanczos", "Filter", "QR", "RR", "Resid")},
+            "max_resid": max(r["resid"][:nev]),
+            "note": "start vectors from cuRAND, so the iteration count may differ from the parity-mode runs"}
 
 
 def sample_text(r):
@@ -345,6 +378,8 @@ def ours(a):
             line["cpu_baseline"] = {"value": r["tflops_per_solve"], "unit": "TFLOP/s", "cores": r["threads"],
                                     "kind": "reference", "sample": sample_text(r),
                                     "filter_phase_tflops": r["tflops_filter_phase"], "host_cores": os.cpu_count()}
+    if not a.no_gpu_reference:
+        line["gpu_reference"] = run_reference_gpu(a.workload)
     print(json.dumps(line))
 
 

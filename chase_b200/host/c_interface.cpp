@@ -699,6 +699,53 @@ extern "C"
         return -1;
     }
 
+    // ---- matrix file I/O (reference chase_c_interface.h:196-214; the un-prefixed names are aliases) -----------------
+#define CB2_IO_API(X, SEQ0, SEQ1, DIST0, DIST1)                                                                        \
+    void p##X##chase_readHam_(const char* filename)                                                                    \
+    {                                                                                                                  \
+        try                                                                                                            \
+        {                                                                                                              \
+            if (DIST1::get().solver)                                                                                   \
+                DIST1::get().solver->loadProblemFromFile(filename);                                                    \
+            else if (DIST0::get().solver)                                                                              \
+                DIST0::get().solver->loadProblemFromFile(filename);                                                    \
+            else if (SEQ1::get().solver)                                                                               \
+                SEQ1::get().solver->loadProblemFromFile(filename);                                                     \
+            else if (SEQ0::get().solver)                                                                               \
+                SEQ0::get().solver->loadProblemFromFile(filename);                                                     \
+        }                                                                                                              \
+        catch (const std::exception& e)                                                                                \
+        {                                                                                                              \
+            std::fprintf(stderr, "%s\n", e.what());                                                                    \
+            g_last.error = e.what();                                                                                   \
+        }                                                                                                              \
+    }                                                                                                                  \
+    void X##chase_readHam_(const char* filename) { p##X##chase_readHam_(filename); }                                   \
+    void p##X##chase_wrtHam_(const char* filename)                                                                     \
+    {                                                                                                                  \
+        try                                                                                                            \
+        {                                                                                                              \
+            if (DIST1::get().solver)                                                                                   \
+                DIST1::get().solver->saveProblemToFile(filename);                                                      \
+            else if (DIST0::get().solver)                                                                              \
+                DIST0::get().solver->saveProblemToFile(filename);                                                      \
+            else if (SEQ1::get().solver)                                                                               \
+                SEQ1::get().solver->saveProblemToFile(filename);                                                       \
+            else if (SEQ0::get().solver)                                                                               \
+                SEQ0::get().solver->saveProblemToFile(filename);                                                       \
+        }                                                                                                              \
+        catch (const std::exception& e)                                                                                \
+        {                                                                                                              \
+            std::fprintf(stderr, "%s\n", e.what());                                                                    \
+            g_last.error = e.what();                                                                                   \
+        }                                                                                                              \
+    }
+    CB2_IO_API(d, SD, SD, PD, PD)
+    CB2_IO_API(s, SS, SS, PS, PS)
+    CB2_IO_API(z, SZ, SZP, PZ, PZP)
+    CB2_IO_API(c, SC, SCP, PC, PCP)
+#undef CB2_IO_API
+
     // ---- communicator bootstrap (include/chase_b200_comm.h) ------------------------------------------------
     int chase_b200_comm_unique_id(void* id_out)
     {

@@ -31,6 +31,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <random>
 #include <stdexcept>
@@ -557,6 +558,31 @@ public:
     {
         if (std::getenv("CHASE_B200_VERBOSE"))
             std::cout << s;
+    }
+
+    // Raw column-major binary matrix files, the reference's format (Matrix::readFromBinaryFile / saveToBinaryFile,
+    // linalg/matrix/matrix.hpp:276-352; ChASEGPU::loadProblemFromFile, chase_gpu.hpp:436-440): N*N elements, no
+    // header.  The file lands in the caller's host H, which the next solve uploads.
+    void loadProblemFromFile(const std::string& filename)
+    {
+        std::ifstream f(filename, std::ios::binary);
+        if (!f.is_open())
+            throw std::runtime_error("chase_b200: cannot open " + filename + " for reading");
+        f.seekg(0, std::ios::end);
+        if ((std::size_t)f.tellg() < N_ * N_ * sizeof(T))
+            throw std::runtime_error("chase_b200: " + filename + " is smaller than the N x N matrix");
+        f.seekg(0, std::ios::beg);
+        for (std::size_t j = 0; j < N_; ++j)
+            f.read(reinterpret_cast<char*>(H_ + j * ldh_), (std::streamsize)(N_ * sizeof(T)));
+        matrix_on_device_ = false;
+    }
+    void saveProblemToFile(const std::string& filename)
+    {
+        std::ofstream f(filename, std::ios::binary);
+        if (!f.is_open())
+            throw std::runtime_error("chase_b200: cannot open " + filename + " for writing");
+        for (std::size_t j = 0; j < N_; ++j)
+            f.write(reinterpret_cast<const char*>(H_ + j * ldh_), (std::streamsize)(N_ * sizeof(T)));
     }
 
     // ---- extras (not part of ChaseBase) ------------------------------------

@@ -40,6 +40,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <random>
 #include <stdexcept>
@@ -596,6 +597,52 @@ public:
     {
         if (grid_.rank == 0 && std::getenv("CHASE_B200_VERBOSE"))
             std::cout << s;
+    }
+
+    // Global matrix files (raw column-major N x N, the reference's format): every rank reads / writes the pieces of
+    // its own local block at their global offsets (reference: MPI-IO darray views for block-cyclic matrices,
+    // linalg/distMatrix/distMatrix.hpp:3117-3196, per-rank seeks for block matrices).  All ranks of one node share the
+    // file; the caller synchronises the ranks between a write and a read.
+    void loadProblemFromFile(const std::string& filename)
+    {
+        if (H_ == nullptr)
+            throw std::runtime_error("chase_b200: no host matrix buffer (device-resident hand-over) to read into");
+        std::ifstream f(filename, std::ios::binary);
+        if (!f.is_open())
+            throw std::runtime_error("chase_b200: cannot open " + filename + " for reading");
+        f.seekg(0, std::ios::end);
+        if ((std::size_t)f.tellg() < N_ * N_ * sizeof(T))
+            throw std::runtime_error("chase_b200: " + filename + " is smaller than the N x N matrix");
+        const auto segs = Dr_.segments(grid_.i);
+        const auto gcols = Dc_.global_indices(grid_.j);
+        for (std::size_t lc = 0; lc < gcols.size(); ++lc)
+            for (const auto& sg : segs)
+            {
+                f.seekg((std::streamoff)(((std::size_t)gcols[lc] * N_ + (std::size_t)sg.g0) * sizeof(T)), std::ios::beg);
+                f.read(reinterpret_cast<char*>(H_ + (std::size_t)sg.l0 + lc * ldh_), (std::streamsize)(sg.len * sizeof(T)));
+            }
+        matrix_on_device_ = false;
+    }
+    void saveProblemToFile(const std::string& filename)
+    {
+        if (H_ == nullptr)
+            throw std::runtime_error("chase_b200: no host matrix buffer (device-resident hand-over) to write");
+        // in | out without trunc: every rank patches its pieces into the shared file (created by whoever is first)
+        {
+            std::ofstream create(filename, std::ios::binary | std::ios::app);
+        }
+        std::fstream f(filename, std::ios::binary | std::ios::in | std::ios::out);
+        if (!f.is_open())
+            throw std::runtime_error("chase_b200: cannot open " + filename + " for writing");
+        const auto segs = Dr_.segments(grid_.i);
+        const auto gcols = Dc_.global_indices(grid_.j);
+        for (std::size_t lc = 0; lc < gcols.size(); ++lc)
+            for (const auto& sg : segs)
+            {
+                f.seekp((std::streamoff)(((std::size_t)gcols[lc] * N_ + (std::size_t)sg.g0) * sizeof(T)), std::ios::beg);
+                f.write(reinterpret_cast<const char*>(H_ + (std::size_t)sg.l0 + lc * ldh_),
+                        (std::streamsize)(sg.len * sizeof(T)));
+            }
     }
 
     // ---- extras ----------------------------------------------------------------

@@ -145,6 +145,23 @@ extern "C"
     CHASE_B200_DIST_PSEUDO_API(z, CHASE_B200_CD, double)
     CHASE_B200_DIST_PSEUDO_API(c, CHASE_B200_CF, float)
 
+    /* Matrix file I/O (reference interface/chase_c_interface.h:196-214): raw column-major N x N binary files, no
+       header (Matrix::readFromBinaryFile / saveToBinaryFile, linalg/matrix/matrix.hpp:276-352).  They act on the host
+       matrix buffer given at init (every rank reads / writes the pieces of its own local block); the next solve uploads
+       it.  The un-prefixed readHam names are aliases, as in the reference. */
+    void pschase_wrtHam_(const char* filename);
+    void pdchase_wrtHam_(const char* filename);
+    void pcchase_wrtHam_(const char* filename);
+    void pzchase_wrtHam_(const char* filename);
+    void pschase_readHam_(const char* filename);
+    void pdchase_readHam_(const char* filename);
+    void pcchase_readHam_(const char* filename);
+    void pzchase_readHam_(const char* filename);
+    void schase_readHam_(const char* filename);
+    void dchase_readHam_(const char* filename);
+    void cchase_readHam_(const char* filename);
+    void zchase_readHam_(const char* filename);
+
     /* ---- chase_b200 additions (introspection for parity tests and benchmarks) ---- */
     /* residuals of the last solve (nev+nex values, ordered like ritzv) */
     void dchase_get_resid_(double* resid);

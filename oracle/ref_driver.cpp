@@ -41,6 +41,12 @@
 
 #include "algorithm/performance.hpp"
 #include "Impl/chase_cpu/chase_cpu.hpp"
+#ifdef REF_GPU
+// chase_ref_gpu_<d|z>: the reference's OWN single-GPU backend (cuBLAS / cuSOLVER / cuRAND), built by `make refgpu`
+// for the same-box GPU baseline of bench.py.  Its start vectors come from cuRAND, so iteration counts
+// differ slightly from the CPU reference / from chase_b200's parity mode.
+#include "Impl/chase_gpu/chase_gpu.hpp"
+#endif
 
 #ifndef REF_T
 #define REF_T double
@@ -155,6 +161,9 @@ int main(int argc, char** argv)
 #ifdef REF_PSEUDO
     const std::size_t ncols = 2 * nevex; // [positive | K-conjugate] halves
     using Backend = chase::Impl::ChASECPU<T, chase::matrix::PseudoHermitianMatrix<T>>;
+#elif defined(REF_GPU)
+    const std::size_t ncols = nevex;
+    using Backend = chase::Impl::ChASEGPU<T>;
 #else
     const std::size_t ncols = nevex;
     using Backend = chase::Impl::ChASECPU<T>;

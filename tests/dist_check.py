@@ -148,6 +148,48 @@ def run_pseudo_case(world, name, grid, layout, major):
                 fails=fails)
 
 
+def run_io_case(world, grid, layout, major):
+    """p?chase_readHam_ / p?chase_wrtHam_ on a grid: every rank reads the pieces of its local block from one global
+    column-major file, solves, and writes them back into a second file, which must equal the first byte for byte."""
+    import tempfile
+
+    import torch.distributed as dist
+
+    N, nev, nex = 256, 24, 16
+    H = co.clement(N, np.float64)
+    H[3, 9] = H[9, 3] = 0.5
+    tmp = tempfile.gettempdir()
+    src, dst = os.path.join(tmp, "chase_b200_io_in.bin"), os.path.join(tmp, "chase_b200_io_out.bin")
+    if world.rank == 0:
+        np.asfortranarray(H).T.tofile(src)
+        if os.path.exists(dst):
+            os.remove(dst)
+    world.barrier()
+    nb = 0 if layout == "block" else 32
+    r, c = grid
+    i, j = cd.grid_coords(r, c, major, world.rank)
+    gr, gc = cd.global_indices(N, r, nb, i), cd.global_indices(N, c, nb, j)
+    fails = []
+    with cd.PChASE(world, N, nev, nex, np.zeros((len(gr), len(gc)), order="F"), grid=grid, major=major, mb=nb, nb=nb) as s:
+        s._lib.pdchase_readHam_(src.encode())
+        if not np.array_equal(s.H, H[np.ix_(gr, gc)]):
+            fails.append("local block read from file differs")
+        res = s.solve(deg=16, tol=1e-10)
+        s._lib.pdchase_wrtHam_(dst.encode())
+    world.barrier()
+    w = np.linalg.eigvalsh(H)[:nev]
+    rel = float(np.max(np.abs(res.ritzv[:nev] - w) / np.abs(w)))
+    if rel > 1e-10:
+        fails.append(f"eigenvalues off by {rel:.2e}")
+    if world.rank == 0 and open(src, "rb").read() != open(dst, "rb").read():
+        fails.append("file written by wrtHam differs from the file read")
+    if world.size > 1:
+        flags = [None] * world.size
+        dist.all_gather_object(flags, fails)
+        fails = [f for fl in flags for f in fl]
+    return dict(case="readHam/wrtHam", grid=f"{r}x{c}", layout=layout, major=major, max_rel_eig=rel, fails=fails)
+
+
 def run_sequence(world, name, grid, layout, major):
     """tests/noinput.cpp-style sequence on a grid: problem 0 random start, then perturbed matrices re-using the
     distributed V / ritzv (mode 'A'); the local host blocks are re-read at every solve."""
@@ -212,6 +254,13 @@ def main():
                 bad += len(r["fails"])
                 if world.rank == 0:
                     print(("FAIL " if r["fails"] else "ok   ") + json.dumps(r), flush=True)
+    for grid in grids[:1]:
+        for layout, major in (("block", "R"), ("cyclic", "C")):
+            r = run_io_case(world, grid, layout, major)
+            results.append(r)
+            bad += len(r["fails"])
+            if world.rank == 0:
+                print(("FAIL " if r["fails"] else "ok   ") + json.dumps(r), flush=True)
     if not a.no_seq:
         for grid in grids[:1]:
             for layout, major in (("block", "R"), ("cyclic", "R")):
