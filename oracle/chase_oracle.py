@@ -3,7 +3,8 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` leg of
 ``bench.py`` may import this module; the product path never does.
 
-It restates, in plain numpy, the Hermitian ChASE solve of the reference:
+It restates, in plain numpy, the Hermitian ChASE solve of the reference (and, at the end of the file, the
+pseudo-Hermitian / BSE solve: algorithm.inc:1834-2220 with ChASECPU<T, PseudoHermitianMatrix<T>>):
 
 * driver      /root/reference/algorithm/algorithm.inc:1376-1788 (``solve``),
               :942-1009 (``filter``), :136-193 (``calc_degrees``),
@@ -641,12 +642,12 @@ def residual_norms(A, V, theta):
 # --------------------------------------------------------------------------
 # Pseudo-Hermitian (BSE) path — kernel-level restatements.
 #
-# H = [[A, B], [-conj(B), -conj(A)]] with S = diag(I, -I) and S H Hermitian positive definite.  The DRIVER of this
-# path (algorithm.inc:1834-2220 solve_pseudo and helpers) is not restated in numpy: the new C++ driver is pinned
-# bit-for-bit against the reference's own driver by oracle/xcheck_driver.cpp, and full solves are pinned by golden
-# traces of the unmodified reference (oracle/_ref/chase_ref_cpu_p{z,c}, tests/golden/pseudo_*.json) and by the
-# reference's golden spectra (tests/golden/bse_fixtures/eigs_*.bin).  The functions below restate the BACKEND
-# arithmetic the CUDA path has to reproduce and are pinned against those spectra in tests/test_oracle_vs_reference.py.
+# H = [[A, B], [-conj(B), -conj(A)]] with S = diag(I, -I) and S H Hermitian positive definite.  The functions below
+# restate the BACKEND arithmetic the CUDA path has to reproduce and are pinned against the reference's golden spectra
+# (tests/golden/bse_fixtures/eigs_*.bin) in tests/test_pseudo_cpu.py; the DRIVER (algorithm.inc:1834-2220 solve_pseudo
+# and helpers) is restated further down (solve_pseudo) and pinned against golden traces of the unmodified reference
+# (oracle/_ref/chase_ref_cpu_p{z,c}, tests/golden/pseudo_*.json).  Independently, the new C++ driver is pinned
+# bit-for-bit against the reference's own driver by oracle/xcheck_driver.cpp.
 # --------------------------------------------------------------------------
 def bse_matrix(N: int, dtype=np.complex128, seed: int = 11, lam_min: float = 1.0, lam_max: float = 100.0,
                coupling: float = 0.3, nrefl: int = 3):
@@ -780,3 +781,375 @@ def qr_pseudo(V: np.ndarray, locked: int, qr=None) -> np.ndarray:
     out = V.copy()
     out[:, locked:ncols - locked] = W[:, 2 * locked:]
     return out
+
+
+# --------------------------------------------------------------------------
+# Pseudo-Hermitian (BSE) path — backend mirror and driver restatement (complex128 / complex64 storage, decisions in
+# the matching real type).  Pinned by tests/test_pseudo_cpu.py against the golden traces of the unmodified reference
+# (tests/golden/pseudo_*.json): identical iteration count, filtered-vector count, HEMM_H2 schedule, lock counts,
+# ApplyKconjugate sequence and swap count; eigenvalues to 1e-10.
+# --------------------------------------------------------------------------
+class OracleBackendPseudo:
+    """numpy mirror of ChASECPU<T, PseudoHermitianMatrix<T>> (chase_cpu.hpp:74-92, 291-851): 2 (nev+nex) columns laid
+    out [locked+ | active | K-conjugates of active | K-conjugates of locked+]."""
+
+    def __init__(self, H: np.ndarray, nev: int, nex: int):
+        self.H = H
+        self.N = H.shape[0]
+        self.nev, self.nex, self.nevex = nev, nex, nev + nex
+        self.nc = 2 * self.nevex
+        self.dtype = H.dtype
+        self.rdtype = _real_dtype(H.dtype)
+        self.V1 = np.zeros((self.N, self.nc), dtype=self.dtype, order="F")
+        self.V2 = np.zeros_like(self.V1)
+        self.ritzv = np.zeros(self.nc, dtype=self.rdtype)
+        self.resid = np.zeros(self.nc, dtype=self.rdtype)
+        self.locked = 0
+        self.trace = Trace()
+        self.qr_variants = []
+
+    def Start(self):
+        self.locked = 0
+
+    def initVecs(self, random: bool):
+        # chase_cpu.hpp:291-326: the CPU stream on all 2 (nev+nex) columns, lower block damped by T(0.001)
+        if random:
+            self.V1 = init_vectors(self.N, self.nc, self.dtype)
+            self.V1[self.N // 2:] *= self.dtype.type(0.001)
+        self.V2[...] = self.V1
+
+    def HEMM_H2(self, block, alpha, beta, gamma, offset_left, offset_right=0):
+        # chase_cpu.hpp:545-590; columns [locked + offset_left, + block - offset_right) as the reference multiplies
+        # them (the trailing offset_left of those are K-conjugate slots rewritten by ApplyKconjugate afterwards)
+        ncols = block - offset_right if offset_right < block else 0
+        self.trace.hemm_calls += 1
+        self.trace.filtered_vecs += 2 * ncols
+        self.trace.add(f"HEMM_H2 {block} {offset_left}")
+        if ncols:
+            s = slice(offset_left + self.locked, offset_left + self.locked + ncols)
+            t = self.dtype.type
+            self.V2[:, s] = t(alpha) * (self.H @ (self.H @ self.V1[:, s])) + t(beta) * self.V2[:, s]
+            self.V2[:, s] += t(gamma) * self.V1[:, s]
+        self.V1, self.V2 = self.V2, self.V1
+
+    def ApplyKconjugate(self, block):
+        # chase_cpu.hpp:592-625
+        self.trace.add(f"ApplyK {block}")
+        c2 = self.nc - self.locked - block
+        self.V1[:, c2:c2 + block] = k_conjugate(self.V1[:, self.locked:self.locked + block])
+
+    def QR(self, fixednev, cond):
+        # chase_cpu.hpp:627-781 (pseudo-Hermitian branches)
+        self.trace.add(f"QR {fixednev} {cond!r}")
+        L, nc = self.locked, self.nc
+        W = np.asfortranarray(np.hstack([flip_lower_half(self.V1[:, :L]), flip_lower_half(self.V1[:, nc - L:]),
+                                         self.V1[:, L:nc - L]]))
+        dbl = self.rdtype == np.float64
+        upper, lower = (1e8, 2e1) if dbl else (1e4, 1e1)
+        if cond > upper:
+            info = shifted_cholqr2(W)
+            self.qr_variants.append("shifted2")
+        elif cond < lower:
+            info = cholqr1(W)
+            self.qr_variants.append("chol1")
+        else:
+            info = cholqr2(W)
+            self.qr_variants.append("chol2")
+        if info != 0:
+            householder_qr(W)
+            self.qr_variants[-1] += "+householder"
+        self.V1[:, L:nc - L] = W[:, 2 * L:]
+        # both panels keep the locked columns (RR swaps the panels); with nothing locked the second panel also holds
+        # the orthonormal block, which LanczosDos reads back (chase_cpu.hpp:757-774)
+        self.V2[:, :L] = self.V1[:, :L]
+        self.V2[:, nc - L:] = self.V1[:, nc - L:]
+        if L == 0:
+            self.V2[...] = self.V1
+
+    def RR(self, block):
+        # cpu/rayleighRitz.hpp:284-392 on the 2 block active columns; writes 2 block Ritz values, block vectors
+        s = slice(self.locked, self.locked + 2 * block)
+        ritz, X = rayleigh_ritz_v2(self.H, self.V1[:, s])
+        self.ritzv[s] = ritz.astype(self.rdtype)
+        self.V2[:, self.locked:self.locked + block] = X
+        self.V1, self.V2 = self.V2, self.V1
+
+    def Resd(self):
+        # chase_cpu.hpp:803-817: first-half active columns only
+        s = slice(self.locked, self.nevex)
+        V = self.V1[:, s]
+        W = self.H @ V - V * self.ritzv[s].astype(self.dtype)
+        self.resid[s] = np.linalg.norm(W, axis=0).astype(self.rdtype)
+
+    def Swap(self, i, j):
+        self.trace.swaps += 1
+        self.V1[:, [i, j]] = self.V1[:, [j, i]]
+
+    def Lock(self, n):
+        self.trace.add(f"Lock {n}")
+        self.locked += n
+
+    def Lanczos(self, M, numvec):
+        Theta, Tau, ritzV, _, _ = lanczos_pseudo(self.H, self.V1, M, numvec)
+        return Theta.astype(self.rdtype), Tau.astype(self.rdtype), ritzV
+
+    def LanczosDos(self, idx, m, ritzV):
+        self.trace.add(f"LanczosDos {idx} {m}")
+        self.V2[:, :idx] = self.V1[:, :m] @ ritzV[:, :idx].astype(self.dtype)
+        self.V1[:, :m] = self.V2[:, :m]
+
+
+def _cheb_rho_c(t):
+    q = np.sqrt(complex(t * t - 1, 0))
+    return max(abs(complex(t, 0) - q), abs(complex(t, 0) + q))
+
+
+def _cluster_factors(ritzv, resid, tol, unconverged, nex, upperb, lowerb):
+    """algorithm.inc:19-135 detect_eigenvalue_clusters (double arithmetic)."""
+    na = unconverged - nex
+    thr = abs(upperb - lowerb) * 1e-6
+    mean_res = float(np.sum(resid[:na])) / na
+    weight = np.minimum(1.0 + np.log(1.0 + resid[:na] / (mean_res + 1e-14)), 2.5)
+    f = np.ones(na)
+    for i in range(na):
+        dist = np.abs(ritzv[i] - ritzv[:na])
+        near = (dist < thr)
+        near[i] = False
+        spatial = 1.0
+        if near.any():
+            density = 0.0
+            for j in np.nonzero(near)[0]:
+                density += weight[j] / (dist[j] + 1e-14)
+            spatial = 1.0 + math.log(1.0 + density * 0.1)
+        c = spatial * weight[i]
+        if near.sum() > 2 and resid[i] > 2.0 * mean_res:
+            c *= 1.2
+        if resid[i] > 10.0 * tol:
+            c *= 1.15
+        f[i] = min(3.0, max(0.5, c))
+    raw = f.copy()
+    for i in range(1, na - 1):
+        f[i] = 0.25 * raw[i - 1] + 0.5 * raw[i] + 0.25 * raw[i + 1]
+    return np.minimum(3.0, np.maximum(0.5, f))
+
+
+def _calc_degrees_pseudo_h2(be, cfg, unconverged, nex, upperb, lowerb, tol, ritzv, resid, residLast, degrees, locked):
+    """algorithm.inc:196-317 (cluster-aware degrees on, the reference default); arrays are views from `locked` on."""
+    factors = _cluster_factors(ritzv, resid, tol, unconverged, nex, upperb, lowerb)
+    c, e = (upperb + lowerb) / 2, (upperb - lowerb) / 2
+    cap = cfg.max_deg
+    for i in range(unconverged):
+        rho = _cheb_rho_c((ritzv[i] * ritzv[i] - c) / e)
+        if not math.isfinite(rho) or rho <= 1:
+            deg = cap
+        else:
+            steps = math.log(resid[i] / tol) / math.log(rho)
+            if not math.isfinite(steps):
+                deg = cap
+            else:
+                deg = int(math.ceil(abs(steps)))
+                deg = int(deg * (factors[i] if i < len(factors) else 1.0))
+                if resid[i] <= tol * 10.0:
+                    if abs(resid[i] - residLast[i]) / (resid[i] + 1e-14) < 0.1:
+                        deg += 6
+                if abs(ritzv[i]) < abs(upperb - lowerb) * 0.1:
+                    deg += 2
+                deg = min(deg + cfg.deg_extra, cap)
+        degrees[i] = deg + (deg % 2)
+    for j in range(unconverged - 1):
+        for k in range(j, unconverged):
+            if degrees[k] < degrees[j]:
+                degrees[[k, j]] = degrees[[j, k]]
+                ritzv[[k, j]] = ritzv[[j, k]]
+                resid[[k, j]] = resid[[j, k]]
+                be.Swap(k + locked, j + locked)
+    return int(degrees[:unconverged].max())
+
+
+def _filter_h2(be, unconverged, degrees, lambda_1, lower, upper):
+    """algorithm.inc:1012-1064."""
+    if lower >= upper:
+        lower, upper = upper, lower
+    c, e = (upper + lower) / 2, (upper - lower) / 2
+    sigma_1 = e / (lambda_1 - c)
+    sigma = sigma_1
+    deg_max = int(degrees[:unconverged].max())
+    a1 = sigma_1 / e
+    be.HEMM_H2(unconverged, a1, 0.0, -a1 * c, 0, 0)
+    s = 0
+    for t in range(2, deg_max + 1):
+        if s >= unconverged:
+            break
+        tau = 1.0 / (2.0 / sigma_1 - sigma)
+        alpha = 2.0 * tau / e
+        be.HEMM_H2(unconverged, alpha, -(sigma * tau), -alpha * c, s, 0)
+        sigma = tau
+        while s < unconverged and degrees[s] <= t:
+            s += 1
+
+
+def _locking_pseudo(be, unconverged, nex, tol, ritzv, resid, residLast, locked, iteration, early):
+    """algorithm.inc:730-816 locking_pseudo_v3 with the identity index the driver passes."""
+    resid_in = resid[:2 * unconverged].copy()
+    open_idx = []
+    converged = 0
+    for k in range(unconverged - nex):
+        j = k
+        early_lock = resid[j] > tol and resid[j] >= residLast[k] and resid[j] <= 1000.0 * tol and iteration >= 4
+        if resid[j] <= tol or early_lock:
+            if early_lock:
+                early.append(float(resid[j]))
+            if j != converged:
+                resid[[j, converged]] = resid[[converged, j]]
+                ritzv[[j, converged]] = ritzv[[converged, j]]
+                be.Swap(j + locked, converged + locked)
+            converged += 1
+        else:
+            open_idx.append(j)
+    open_idx += list(range(unconverged - nex, unconverged))
+    for i in range(converged, unconverged):
+        residLast[i] = resid_in[open_idx[i - converged]]
+    return converged
+
+
+def _lanczos_for_h2(be, cfg, N, numvec, m, nevex, ritzv_):
+    """algorithm.inc:1217-1373 (mode = true).  Returns b_sup = (max |theta|)^2."""
+    Theta, Tau, ritzV = be.Lanczos(m, numvec)
+    nt = numvec * m
+    ThetaSorted = np.sort(Theta.astype(np.float64))
+    sigma = 0.25
+    thresh = 2 * sigma * sigma / 10
+    absT = np.abs(Theta)
+    i_min = int(np.argmin(absT))  # first minimum, like the reference's strict '<' scan
+    mu_1 = Theta[i_min] * Theta[i_min]
+    b_sup = absT.max() ** 2
+    search = min(1.0, max(0.0, (N / 2 - cfg_nev(be) - be.nex - 1) / N))
+    lam_q = ThetaSorted[nt - 1]
+    prev = 0.0
+    Td, Taud = Theta.astype(np.float64), Tau.astype(np.float64)
+    for i in range(nt):
+        x = ThetaSorted[i] - Td
+        g = 0.5 * (1 + np.array([math.erf(v / math.sqrt(2 * sigma * sigma)) for v in x]))
+        curr = float(np.sum(np.where(x < -thresh, 0.0, np.where(x > thresh, Taud, Taud * g)))) / numvec
+        if curr > search:
+            if abs(curr - search) < abs(prev - search):
+                lam_q = ThetaSorted[i]
+            else:
+                lam_q = ThetaSorted[i - 1] if i > 0 else ThetaSorted[i]
+            break
+        prev = curr
+        lam_q = ThetaSorted[i]
+    lam_q = be.rdtype.type(lam_q)
+    mu_q = lam_q * lam_q
+    last = Theta[(numvec - 1) * m:]
+    idx = 0
+    for i in range(m):
+        if last[i] > lam_q:
+            idx = i - 1
+            break
+        idx = i + 1
+    idx = max(idx, 0)
+    if idx > 0:
+        be.LanczosDos(idx, m, ritzV)
+    ritzv_[:idx] = last[:idx] * last[:idx]
+    ritzv_[idx:nevex - 1] = mu_1
+    ritzv_[nevex - 1] = mu_q
+    for i in range(1, idx):
+        j = i * (nevex // idx)
+        be.Swap(i, j)
+        ritzv_[[i, j]] = ritzv_[[j, i]]
+    return be.rdtype.type(b_sup)
+
+
+def cfg_nev(be):
+    return be.nev
+
+
+def solve_pseudo(be: OracleBackendPseudo, cfg: Config, upperb_scale: float = 1.0) -> Trace:
+    """algorithm.inc:1834-2220 (random start vectors)."""
+    N, nev, nex, nevex = be.N, be.nev, be.nex, be.nevex
+    tr = be.trace
+    be.Start()
+    unconverged = nevex
+    deg = min(cfg.deg + cfg.deg % 2, cfg.max_deg)
+    degrees_ = np.zeros(2 * nevex, dtype=np.int64)
+    degrees_[:unconverged] = deg
+    tol = cfg.tol
+    big = np.finfo(be.rdtype).max
+    be.resid[:] = big
+    residLast_ = np.full(2 * nevex, big, dtype=be.rdtype)
+    be.initVecs(True)
+    be.QR(0, 1.0)
+    lanczos_iter = min(nevex, N // 2, cfg.lanczos_iter)
+    lanczos_iter -= lanczos_iter % 2
+    upperb = _lanczos_for_h2(be, cfg, N, cfg.num_lanczos, lanczos_iter, nevex, be.ritzv)
+    lambda_1 = be.ritzv[:nevex - 1].min()
+    lower = be.ritzv[nevex - 1]
+    b_sup = upperb * upperb_scale if upperb > 0 else upperb / upperb_scale
+    next_lower = lower
+    lower = lower * cfg.decaying_rate
+    locked = iteration = 0
+    early = []
+    while locked < nev and unconverged > 0 and iteration < cfg.max_iter:
+        ritzv, resid, residLast, degrees = be.ritzv[locked:], be.resid[locked:], residLast_[locked:], degrees_[locked:]
+        if iteration > 0:
+            next_lower = next_lower * next_lower
+            if lambda_1 < next_lower < lower:
+                lower = next_lower
+        if cfg.opt and iteration != 0:
+            deg = _calc_degrees_pseudo_h2(be, cfg, unconverged, nex, b_sup, lower, tol, ritzv, resid, residLast,
+                                          degrees, locked)
+        _filter_h2(be, unconverged, degrees, lambda_1, lower, b_sup)
+        be.ApplyKconjugate(unconverged)
+        cc, ee = (b_sup + lower) / 2, (b_sup - lower) / 2
+        if ee <= 0:
+            ee = abs(lower - b_sup) / 2
+        t_1 = (lambda_1 - cc) / ee
+        t_k = (ritzv[0] * ritzv[0] - cc) / ee if iteration > 0 else t_1
+        rho_1, rho_k = _cheb_rho_c(t_1), _cheb_rho_c(t_k)
+        deg_max = int(degrees[:unconverged].max())
+        with np.errstate(over="ignore"):
+            cond = be.rdtype.type(rho_k) ** be.rdtype.type(degrees[0]) * be.rdtype.type(rho_1) ** be.rdtype.type(
+                deg_max - degrees[0])
+        be.QR(locked, float(cond))
+        be.RR(unconverged)
+        tr.iterations += 1
+        be.Resd()
+        order = sorted(range(unconverged), key=lambda a: ritzv[a])
+        next_lower = ritzv[order[int(unconverged * 0.95) - 1]] * cfg.decaying_rate
+        new_conv = _locking_pseudo(be, unconverged, nex, tol, ritzv, resid, residLast, locked, iteration, early)
+        if new_conv > 0:
+            be.ApplyKconjugate(new_conv)
+        be.Lock(new_conv)
+        locked += new_conv
+        unconverged -= new_conv
+        iteration += 1
+    # positive Ritz values first (ascending), then the rest (ascending); swaps along the permutation cycles
+    n = locked + unconverged
+    rz, rs = be.ritzv, be.resid
+    perm = sorted(range(n), key=lambda i: (not (rz[i] > 0), rz[i]))
+    visited = [False] * n
+    for i in range(n):
+        if visited[i] or perm[i] == i:
+            continue
+        cyc, cur = [], i
+        while not visited[cur]:
+            visited[cur] = True
+            cyc.append(cur)
+            cur = perm[cur]
+        r0, s0 = rz[i], rs[i]
+        for k in range(len(cyc) - 1):
+            rz[cyc[k]] = rz[cyc[k + 1]]
+            rs[cyc[k]] = rs[cyc[k + 1]]
+            be.Swap(cyc[k], cyc[k + 1])
+        rz[cyc[-1]], rs[cyc[-1]] = r0, s0
+    return tr
+
+
+def solve_problem_pseudo(H: np.ndarray, nev: int, nex: int, cfg: Config | None = None):
+    """-> (ritzv[:nev+nex], resid[:nev+nex], V (all 2 (nev+nex) columns), trace, backend)."""
+    H = np.asfortranarray(H.copy())
+    cfg = cfg or Config.for_dtype(H.dtype)
+    be = OracleBackendPseudo(H, nev, nex)
+    tr = solve_pseudo(be, cfg)
+    return be.ritzv[:nev + nex].copy(), be.resid[:nev + nex].copy(), be.V1.copy(), tr, be

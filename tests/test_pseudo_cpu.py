@@ -154,3 +154,37 @@ def test_benchmark_bse_block_generator_equals_oracle_matrix():
     assert np.array_equal(lam, lam2)
     blkT, _ = bd.bse_local_block(N, np.arange(N), np.arange(N), "cpu", transposed=True)
     assert np.abs(blkT.numpy().T - H).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["pseudo_bse_z_N200", "pseudo_synth_z_N600", "pseudo_synth_z_N600_noopt"])
+def test_numpy_restatement_of_solve_pseudo_matches_reference_trace(name):
+    """oracle.solve_pseudo (numpy restatement of algorithm.inc:1834-2220 + ChASECPU<PseudoHermitianMatrix>) against the
+    golden trace of the unmodified reference: identical decisions, eigenvalues to 1e-10."""
+    g = load(name)
+    p = g["problems"][0]
+    ref = parse_trace(p["trace"])
+    kind, arg = g["matrix"].split(":", 1)
+    if kind == "bse_fixture":
+        H = _fixture(arg, np.complex128, g["N"])
+    else:
+        H, _ = co.bse_matrix(g["N"], seed=int(arg))
+    cfg = co.Config.for_dtype(np.complex128)
+    cfg.tol, cfg.deg, cfg.opt = g["tol"], g["deg"], bool(g["opt"])
+    if "numlanczos" in g:
+        cfg.num_lanczos, cfg.lanczos_iter = g["numlanczos"], g["lanczositer"]
+    rv, rs, V, tr, be = co.solve_problem_pseudo(H, g["nev"], g["nex"], cfg)
+    sched = [tuple(int(x) for x in c.split()[1:3]) for c in tr.calls if c.startswith("HEMM_H2")]
+    locks = [int(c.split()[1]) for c in tr.calls if c.startswith("Lock")]
+    applyk = [int(c.split()[1]) for c in tr.calls if c.startswith("ApplyK")]
+    dos = [tuple(int(x) for x in c.split()[1:3]) for c in tr.calls if c.startswith("LanczosDos")]
+    assert tr.iterations == p["iterations"]
+    assert tr.filtered_vecs == p["filtered_vecs"]
+    assert sched == [h[:2] for h in ref["hemm_h2"]]
+    assert locks == ref["locks"]
+    assert applyk == ref["applyk"]
+    assert dos == ([ref["dos"]] if ref["dos"] else [])
+    assert tr.swaps == p["swaps"]
+    nev = g["nev"]
+    refv = np.array(p["ritzv"][:nev])
+    assert np.max(np.abs(rv[:nev] - refv) / np.abs(refv)) < 1e-10
+    assert np.all(rs[:nev] < 1000 * g["tol"])
