@@ -261,6 +261,17 @@ __global__ void __launch_bounds__(1024) lanczos_step_kernel(long long rows, int 
     }
 }
 
+// ---- FP32 storage on the FP64 TMA pipeline ----------------------------------------------------------------------
+// dst (wide: double / complex<double>) <- src (float / complex<float>) and back; rows x cols, column-major
+template <class TS, class TD>
+__global__ void convert_kernel(long long rows, long long cols, const TS* src, long long lds, TD* dst, long long ldd)
+{
+    for (long long j = blockIdx.y; j < cols; j += gridDim.y)
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+             i += (long long)gridDim.x * blockDim.x)
+            dst[i + j * ldd] = narrow<TD>(widen(src[i + j * lds]));
+}
+
 // ---- pseudo-Hermitian (BSE) helpers ------------------------------------------------------------------------------
 // H = [[A, B], [-conj(B), -conj(A)]], S = diag(I, -I).  Reference counterparts: flipSign.cu (S X), conjugate.cu +
 // lacpy (K-conjugation, Impl/chase_gpu/chase_gpu.hpp:718-742), pseudo_hermitian_lanczos_diag.cu and the S-inner-

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <vector>
 
@@ -47,6 +48,35 @@ template <class T>
 int hemm_rect_impl(int ta, int64_t M, int64_t K, int64_t k, double are, double aim, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double bre, double bim, void* C, int64_t ldc, double shift,
                    const double* theta, void* stream);
+
+// FP32-storage matrices with a registered FP64 copy (chase_b200_widen_register): the filter product then runs on the
+// TMA + DMMA kernel of the wide type, with the panels widened into / narrowed out of a scratch area per call
+// (O(N k) traffic against O(N^2 k) flop).  Keyed by the base pointer of the narrow matrix.
+struct WideCopy
+{
+    void* wide = nullptr;
+    int64_t ld = 0, rows = 0, cols = 0;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+inline std::map<const void*, WideCopy>& wide_registry()
+{
+    static std::map<const void*, WideCopy> r;
+    return r;
+}
+template <class T>
+struct WideOf;
+template <>
+struct WideOf<float>
+{
+    using type = double;
+};
+template <>
+struct WideOf<cxf>
+{
+    using type = cxd;
+};
+inline dim3 grid2d(int64_t rows, int64_t cols);
 
 template <class T>
 int gemm_impl(int ta, int tb, int64_t M, int64_t N, int64_t K, double are, double aim, const void* A, int64_t lda,
@@ -126,6 +156,33 @@ int hemm_rect_impl(int ta, int64_t M, int64_t K, int64_t k, double are, double a
         if (K > 0 && hemm_tma_supported<T>(M, K, k, A, lda, B, ldb, C, ldc))
             return hemm_tma_launch<T>(ta != 0, M, K, k, alpha, (const T*)A, lda, (const T*)B, ldb, beta, (T*)C, ldc,
                                       shift, theta, S(stream));
+    }
+    else
+    {
+        using TW = typename WideOf<T>::type;
+        auto it = wide_registry().find(A);
+        if (it != wide_registry().end() && K > 0)
+        {
+            const WideCopy& w = it->second;
+            const int64_t ldbw = (K + 15) / 16 * 16, ldcw = (M + 15) / 16 * 16;
+            TW* Bw = (TW*)w.scratch;
+            TW* Cw = Bw + ldbw * k;
+            const bool fits = (size_t)(ldbw + ldcw) * (size_t)k * sizeof(TW) <= w.scratch_bytes && w.ld == lda;
+            if (fits && hemm_tma_supported<TW>(M, K, k, w.wide, lda, Bw, ldbw, Cw, ldcw))
+            {
+                cudaStream_t st = S(stream);
+                convert_kernel<T, TW><<<grid2d(K, k), 256, 0, kcount(st)>>>(K, k, (const T*)B, ldb, Bw, ldbw);
+                if (cnonzero(beta))
+                    convert_kernel<T, TW><<<grid2d(M, k), 256, 0, kcount(st)>>>(M, k, (const T*)C, ldc, Cw, ldcw);
+                int rc = hemm_tma_launch<TW>(ta != 0, M, K, k, alpha, (const TW*)w.wide, lda, Bw, ldbw, beta, Cw, ldcw,
+                                             shift, theta, st);
+                if (rc)
+                    return rc;
+                convert_kernel<TW, T><<<grid2d(M, k), 256, 0, kcount(st)>>>(M, k, Cw, ldcw, (T*)C, ldc);
+                CB2_CUDA_OK(cudaGetLastError());
+                return 0;
+            }
+        }
     }
     GemmArgs<T> p{};
     p.M = M;
@@ -855,6 +912,48 @@ extern "C" int chase_b200_tridiag_eig(int n, int batch, const double* d, const d
     if (n > JSMALL_MAX)
         return -2;
     jacobi_small_tridiag_kernel<<<batch, 256, 0, kcount(S(st))>>>(n, d, e, ldde, w, Z, nullptr);
+    CB2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chase_b200_widen_register(const void* A, void* A_wide, int64_t ld, int64_t rows, int64_t cols,
+                                         void* scratch, size_t scratch_bytes)
+{
+    if (!A || !A_wide)
+        return -2;
+    WideCopy w;
+    w.wide = A_wide;
+    w.ld = ld;
+    w.rows = rows;
+    w.cols = cols;
+    w.scratch = scratch;
+    w.scratch_bytes = scratch_bytes;
+    wide_registry()[A] = w;
+    return 0;
+}
+extern "C" int chase_b200_widen_unregister(const void* A)
+{
+    wide_registry().erase(A);
+    return 0;
+}
+// refresh the FP64 copy after the narrow matrix changed (upload); type: 's' or 'c'
+extern "C" int chase_b200_widen_sync(char type, const void* A, void* stream)
+{
+    auto it = wide_registry().find(A);
+    if (it == wide_registry().end())
+        return -2;
+    const WideCopy& w = it->second;
+    if (w.rows <= 0 || w.cols <= 0)
+        return 0;
+    cudaStream_t st = S(stream);
+    if (type == 's')
+        convert_kernel<float, double><<<grid2d(w.rows, w.cols), 256, 0, kcount(st)>>>(w.rows, w.cols, (const float*)A, w.ld,
+                                                                                      (double*)w.wide, w.ld);
+    else if (type == 'c')
+        convert_kernel<cxf, cxd><<<grid2d(w.rows, w.cols), 256, 0, kcount(st)>>>(w.rows, w.cols, (const cxf*)A, w.ld,
+                                                                                 (cxd*)w.wide, w.ld);
+    else
+        return -2;
     CB2_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -136,10 +136,23 @@ public:
             perm_[i] = (int)i;
         const char* e = std::getenv("CHASE_B200_DEVICE_RNG");
         device_rng_ = e && std::atoi(e) != 0;
+        // FP32 storage: keep an FP64 copy of A so that the filter products run on the TMA + DMMA kernel (the generic
+        // kernel reaches 19 of 37 TFLOP/s); costs 2x the matrix memory, CHASE_B200_FP32_WIDEN=0 turns it off
+        const char* w = std::getenv("CHASE_B200_FP32_WIDEN");
+        if (sizeof(R) == 4 && !(w && std::atoi(w) == 0))
+        {
+            wide_scratch_bytes_ = 2 * ld_ * nc_ * 2 * sizeof(T);
+            dHw_ = alloc<unsigned char>(ld_ * N_ * 2 * sizeof(T));
+            wide_scratch_ = alloc<unsigned char>(wide_scratch_bytes_);
+            chase_b200_widen_register(dH_, dHw_, (int64_t)ld_, (int64_t)N_, (int64_t)N_, wide_scratch_,
+                                      wide_scratch_bytes_);
+        }
     }
     ChASEGPU(const ChASEGPU&) = delete;
     ~ChASEGPU() override
     {
+        if (dHw_)
+            chase_b200_widen_unregister(dH_);
         for (void* p : allocs_)
             cudaFree(p);
         if (stream_)
@@ -191,6 +204,8 @@ public:
             CB2_CHECK(cudaMemcpy2DAsync(dH_, ld_ * sizeof(T), H_, ldh_ * sizeof(T), N_ * sizeof(T), N_,
                                         cudaMemcpyHostToDevice, stream_));
             matrix_on_device_ = true;
+            if (dHw_)
+                CB2_KCHECK(chase_b200_widen_sync(kCplx ? 'c' : 's', dH_, stream_));
         }
         reset_perm();
         shift_ = 0.0;
@@ -913,6 +928,8 @@ private:
     std::size_t ld_ = 0, ldg_ = 0;
     T *dH_ = nullptr, *dV1_ = nullptr, *dV2_ = nullptr, *dW_ = nullptr, *dG_ = nullptr, *dZ_ = nullptr;
     T *dM_ = nullptr, *dRinv_ = nullptr, *dT_ = nullptr; // pseudo-Hermitian RR only
+    unsigned char *dHw_ = nullptr, *wide_scratch_ = nullptr; // FP64 copy of an FP32 matrix + panel scratch
+    std::size_t wide_scratch_bytes_ = 0;
     double* ones_ = nullptr;
     T* dV0_ = nullptr; // device copy of the reference start block (parity mode), filled at the first random solve
     unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr, *hh_ws_ = nullptr;

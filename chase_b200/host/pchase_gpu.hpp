@@ -133,10 +133,22 @@ public:
         CB2_CHECK(cudaMemsetAsync(dTheta_, 0, nc_ * sizeof(double), stream_));
         const char* e = std::getenv("CHASE_B200_DEVICE_RNG");
         device_rng_ = e && std::atoi(e) != 0;
+        // FP32 storage: FP64 copy of the local block for the TMA + DMMA filter kernel (see ChASEGPU)
+        const char* w = std::getenv("CHASE_B200_FP32_WIDEN");
+        if (sizeof(R) == 4 && !(w && std::atoi(w) == 0))
+        {
+            wide_scratch_bytes_ = (ldv_ + ldw_) * nc_ * 2 * sizeof(T);
+            dHw_ = alloc<unsigned char>(lda_ * std::max<std::size_t>(n_loc_, 1) * 2 * sizeof(T));
+            wide_scratch_ = alloc<unsigned char>(wide_scratch_bytes_);
+            chase_b200_widen_register(dH_, dHw_, (int64_t)lda_, (int64_t)m_loc_, (int64_t)n_loc_, wide_scratch_,
+                                      wide_scratch_bytes_);
+        }
     }
     pChASEGPU(const pChASEGPU&) = delete;
     ~pChASEGPU() override
     {
+        if (dHw_)
+            chase_b200_widen_unregister(dH_);
         cudaStreamSynchronize(stream_);
         for (void* p : allocs_)
             cudaFree(p);
@@ -199,6 +211,12 @@ public:
             CB2_CHECK(cudaMemcpy2DAsync(dH_, lda_ * sizeof(T), H_, ldh_ * sizeof(T), m_loc_ * sizeof(T), n_loc_,
                                         cudaMemcpyHostToDevice, stream_));
             matrix_on_device_ = true;
+            wide_valid_ = false;
+        }
+        if (dHw_ && !wide_valid_)
+        {
+            CB2_KCHECK(chase_b200_widen_sync(kCplx ? 'c' : 's', dH_, stream_));
+            wide_valid_ = true;
         }
         reset_perm();
         next_ = NextOp::bAc;
@@ -209,6 +227,11 @@ public:
     void Shift(T c, bool isunshift = false) override
     {
         CB2_KCHECK(KK::shift_diag_list((int64_t)ndiag_, diag_lin_, dH_, (double)std::real(c), stream_));
+        if (dHw_) // the FP64 copy of an FP32 block follows (same linear indices)
+        {
+            using TW = typename std::conditional<kCplx, std::complex<double>, double>::type;
+            CB2_KCHECK(b200::K<TW>::shift_diag_list((int64_t)ndiag_, diag_lin_, dHw_, (double)std::real(c), stream_));
+        }
         if (isunshift)
             next_ = NextOp::bAc;
     }
@@ -667,7 +690,11 @@ public:
     cudaStream_t stream() const { return stream_; }
     T* device_H() { return dH_; }
     std::size_t device_lda() const { return lda_; }
-    void mark_matrix_on_device() { matrix_on_device_ = true; }
+    void mark_matrix_on_device()
+    {
+        matrix_on_device_ = true;
+        wide_valid_ = false;
+    }
 
 private:
     enum class NextOp
@@ -1162,6 +1189,9 @@ private:
       *dZ_ = nullptr;
     T* dW_[4] = {nullptr, nullptr, nullptr, nullptr};
     T *dM_ = nullptr, *dRinv_ = nullptr, *dT_ = nullptr, *dFull_ = nullptr; // pseudo-Hermitian only
+    unsigned char *dHw_ = nullptr, *wide_scratch_ = nullptr; // FP64 copy of an FP32 local block + panel scratch
+    std::size_t wide_scratch_bytes_ = 0;
+    bool wide_valid_ = false;
     double* ones_ = nullptr;
     T* dV0_ = nullptr; // device copy of this rank's rows of the reference start block (parity mode)
     unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr, *hh_ws_ = nullptr;

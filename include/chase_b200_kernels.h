@@ -158,6 +158,16 @@ extern "C"
     int chase_b200_tridiag_eig(int n, int batch, const double* d_dev, const double* e_dev, int ldde, double* w_dev,
                                double* Z_dev, void* stream);
 
+    /* FP32 storage on the FP64 TMA pipeline: register an FP64 copy A_wide (same ld, caller-owned, device) of the
+       float / complex<float> matrix A plus a scratch area; chase_b200_hemm[_rect]_{s,c} calls whose A is this pointer
+       then widen their panels into the scratch, run the TMA + DMMA kernel of the wide type on A_wide and narrow the
+       result back (needs scratch_bytes >= (roundup16(K) + roundup16(M)) * k * sizeof(wide element)).
+       chase_b200_widen_sync(type 's' | 'c') re-converts A -> A_wide after A changed.  Host-side registry, one entry
+       per matrix; unregister before freeing. */
+    int chase_b200_widen_register(const void* A, void* A_wide, int64_t ld, int64_t rows, int64_t cols, void* scratch,
+                                  size_t scratch_bytes);
+    int chase_b200_widen_unregister(const void* A);
+    int chase_b200_widen_sync(char type, const void* A, void* stream);
     size_t chase_b200_trsm_ws_bytes(int64_t n, int elem_bytes);
     size_t chase_b200_hhqr_ws_bytes(int64_t rows, int64_t n, int elem_bytes);
     size_t chase_b200_heev_ws_bytes(int64_t n, int is_complex);
