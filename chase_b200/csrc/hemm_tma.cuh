@@ -122,6 +122,7 @@ struct HemmParams
     const double* theta; // per-column shift
     int tiles_m, tiles_n;
     long long span;      // k-blocks per CTA (stream-K); a multiple of nkt means whole tiles only
+    int remap;           // != 0: virtual -> raster tile index through hemm_tile_remap (stream-K launches)
     double* scratch;     // gridDim.x slots of BM*BN accumulators for incomplete tiles
     unsigned* flags;     // one per CTA: epoch of the launch whose head part is parked in the slot
     unsigned epoch;
@@ -138,6 +139,30 @@ struct HemmSpan
     long long tile;
     int kt_begin, kt_end;
 };
+
+// L2 locality of the stream-K walk.  Spans are contiguous in the tile index, so with the plain n-fastest raster every
+// CTA streams "its own" ~T/G consecutive tiles = one row block of A after the other, the G co-resident CTAs touch G
+// different row blocks at any time and nothing is shared in L2 (measured at N=20000, k=1400: 62 GB of DRAM reads for
+// 3.9 GB of operands).  The spans therefore walk a VIRTUAL tile index v, mapped to the raster index r by a bijection
+// that puts the s-th tile of every CTA next to each other: with start(c) = floor(c T / G) (first virtual tile of CTA
+// c), q = floor(T / G), v = start(c) + s:
+//     r = s G + c                      for s < q      (all CTAs have a tile at position s)
+//     r = q G + (start(c) - c q)       for s = q      (only the CTAs with q + 1 tiles; rank among those)
+// so the CTAs that run position s at the same time cover G consecutive raster tiles (13 row blocks x 11 column tiles
+// at C2) and share each A row block tiles_n-fold, like a wave of the data-parallel schedule.  Depends on v only, so
+// the two CTAs that share a split tile agree on it.
+__host__ __device__ inline long long hemm_tile_remap(long long v, long long T, long long G)
+{
+    if (G <= 1 || T <= G)
+        return v;
+    long long c = (v * G) / T;
+    while (c + 1 < G && ((c + 1) * T) / G <= v)
+        ++c;
+    while (c > 0 && (c * T) / G > v)
+        --c;
+    const long long start = (c * T) / G, q = T / G, s_ = v - start;
+    return (s_ < q) ? s_ * G + c : q * G + (start - c * q);
+}
 
 template <class T, bool TA>
 __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
@@ -197,7 +222,9 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
             for (long long hi = it_end; hi > it_begin;)
             {
                 const HemmSpan sp = next_part(hi);
-                const int tn = (int)(sp.tile % p.tiles_n), tm = (int)(sp.tile / p.tiles_n);
+                const long long rt = p.remap ? hemm_tile_remap(sp.tile, (long long)p.tiles_m * p.tiles_n, gridDim.x)
+                                             : sp.tile;
+                const int tn = (int)(rt % p.tiles_n), tm = (int)(rt / p.tiles_n);
                 const int m0 = tm * BM, n0 = tn * BN;
                 for (int kt = sp.kt_begin; kt < sp.kt_end; ++kt, ++it)
                 {
@@ -273,7 +300,8 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     {
         const HemmSpan sp = next_part(hi);
         hi -= (sp.kt_end - sp.kt_begin);
-        const int tn = (int)(sp.tile % p.tiles_n), tm = (int)(sp.tile / p.tiles_n);
+        const long long rt = p.remap ? hemm_tile_remap(sp.tile, (long long)p.tiles_m * p.tiles_n, gridDim.x) : sp.tile;
+        const int tn = (int)(rt % p.tiles_n), tm = (int)(rt / p.tiles_n);
         const long long m0 = (long long)tm * BM, n0 = (long long)tn * BN;
 
         double accr[NJ][MI][2];
@@ -572,6 +600,12 @@ inline HemmScratch* hemm_scratch(int dev, cudaStream_t st, int sms)
         return nullptr;
     return &(pool[key] = sc);
 }
+// CHASE_B200_HEMM_REMAP=0 walks the plain raster (diagnostics); read at every launch
+inline bool hemm_remap_disabled()
+{
+    const char* e = getenv("CHASE_B200_HEMM_REMAP");
+    return e && atoi(e) == 0;
+}
 inline bool hemm_streamk_disabled()
 {
     static int v = -1;
@@ -645,11 +679,13 @@ inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Tr
     const long long ntiles = (long long)p.tiles_m * p.tiles_n;
     const long long nkt = (K + CF::BK - 1) / CF::BK;
     int grid;
+    p.remap = 0;
     if (ntiles >= sms && !hemm_streamk_disabled())
     {
         // stream-K: equal spans of k-blocks, at most one incomplete tile at each end of a span
         grid = sms;
         p.span = (ntiles * nkt + grid - 1) / grid;
+        p.remap = hemm_remap_disabled() ? 0 : 1;
     }
     else
     {

@@ -1023,6 +1023,11 @@ extern "C" double chase_b200_dmma_peak(int iters, void* st)
 
 extern "C" unsigned long long chase_b200_launch_count(void) { return launch_counter(); }
 
+extern "C" long long chase_b200_hemm_tile_remap(long long v, long long ntiles, long long nctas)
+{
+    return hemm_tile_remap(v, ntiles, nctas);
+}
+
 extern "C" int chase_b200_hemm_profile_enable(int on)
 {
     g_hprof.on = (on != 0);

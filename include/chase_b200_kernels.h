@@ -176,6 +176,9 @@ extern "C"
     /* FP64 tensor-pipe microbenchmark: runs `iters` register-resident DMMA.8x8x4 per warp on every SM and
        returns the achieved FLOP/s (the roofline denominator for the filter; MEASURED_PEAKS.json has no FP64). */
     double chase_b200_dmma_peak(int iters, void* stream);
+    /* Virtual -> raster tile index of the stream-K filter HEMM (host copy of the device function, for tests):
+       a bijection on [0, ntiles) that places the s-th tile of every CTA next to each other (L2 sharing of A). */
+    long long chase_b200_hemm_tile_remap(long long v, long long ntiles, long long nctas);
     /* Number of product kernels launched by this library so far (process-wide; bench.py's gpu_launches). */
     unsigned long long chase_b200_launch_count(void);
     /* Per-launch CUDA-event timing of the filter HEMM kernel on its launching stream.  enable(1) resets and

@@ -40,3 +40,22 @@ def test_round_robin_pairing_covers_every_pair_once():
                 seen.add((min(p, q), max(p, q)))
             assert len(used) == np_
         assert len(seen) == np_ * (np_ - 1) // 2
+
+
+def test_hemm_tile_remap_is_a_bijection_with_wave_locality():
+    """csrc/hemm_tma.cuh: hemm_tile_remap — the stream-K spans walk a virtual tile index; the map to the raster index
+    must be a bijection for every (tiles, CTAs) and must put the s-th tiles of all CTAs next to each other."""
+    from chase_b200 import lib
+
+    f = lib().chase_b200_hemm_tile_remap
+    f.restype = ctypes.c_longlong
+    f.argtypes = [ctypes.c_longlong] * 3
+    for G in (1, 2, 7, 148):
+        for T in list(range(1, 40)) + [147, 148, 149, 295, 296, 1727, 1728, 157 * 22, 5000]:
+            r = [f(v, T, G) for v in range(T)]
+            assert sorted(r) == list(range(T)), (T, G)
+    # C2 shape: 1727 tiles on 148 CTAs; position s of every CTA -> 148 consecutive raster tiles
+    T, G = 1727, 148
+    for s in range(T // G):
+        block = sorted(f((c * T) // G + s, T, G) for c in range(G))
+        assert block == list(range(s * G, (s + 1) * G))
