@@ -123,6 +123,8 @@ struct HemmParams
     int tiles_m, tiles_n;
     long long span;      // k-blocks per CTA (stream-K); a multiple of nkt means whole tiles only
     int remap;           // != 0: virtual -> raster tile index through hemm_tile_remap (stream-K launches)
+    long long sk_tiles;  // tiles covered by the stream-K phase (all of them unless the hybrid schedule is on)
+    int dp_waves;        // whole-tile waves after the stream-K phase (tile = sk_tiles + w * gridDim.x + blockIdx.x)
     double* scratch;     // gridDim.x slots of BM*BN accumulators for incomplete tiles
     unsigned* flags;     // one per CTA: epoch of the launch whose head part is parked in the slot
     unsigned epoch;
@@ -164,6 +166,51 @@ __host__ __device__ inline long long hemm_tile_remap(long long v, long long T, l
     return (s_ < q) ? s_ * G + c : q * G + (start - c * q);
 }
 
+// The sequence of tile parts one CTA executes; producer and consumer walk it in lock-step, and the host test
+// (chase_b200_hemm_walk) replays it on the CPU.
+//   phase 1 (stream-K): the first sk_tiles tiles x nkt k-blocks are cut into G equal spans; CTA b walks its span
+//            [b span, (b+1) span) from the TOP, so a head part (kt_end < nkt, parked for CTA b+1) comes first and a
+//            tail part (kt_begin > 0, waits for CTA b-1) last.  span >= nkt => at most two parts per tile.
+//   phase 2 (data-parallel, dp_waves > 0): whole tiles sk_tiles + w G + b, w = 0 .. dp_waves-1.  All CTAs enter this
+//            phase after the same number of k-blocks, so CTAs that share a row block of A read the same k range at
+//            the same time (L2 sharing like a plain persistent schedule); phase 1 only absorbs the ragged last wave.
+struct HemmWalk
+{
+    long long it_begin, hi, sk_tiles, G, b;
+    int nkt, dp_waves, w, remap;
+    __host__ __device__ HemmWalk(long long b_, long long G_, long long span, long long sk_tiles_, int nkt_, int dp_waves_,
+                                 int remap_)
+        : sk_tiles(sk_tiles_), G(G_), b(b_), nkt(nkt_), dp_waves(dp_waves_), w(0), remap(remap_)
+    {
+        const long long total = sk_tiles * nkt;
+        it_begin = b * span < total ? b * span : total;
+        hi = it_begin + span < total ? it_begin + span : total;
+    }
+    // next part: raster tile index and k-block range; false when the CTA is done
+    __host__ __device__ bool next(HemmSpan& sp)
+    {
+        if (hi > it_begin)
+        {
+            const long long vt = (hi - 1) / nkt, first = vt * nkt;
+            const long long lo = it_begin > first ? it_begin : first;
+            sp.kt_begin = (int)(lo - first);
+            sp.kt_end = (int)(hi - first);
+            sp.tile = remap ? hemm_tile_remap(vt, sk_tiles, G) : vt;
+            hi = lo;
+            return true;
+        }
+        if (w < dp_waves)
+        {
+            sp.tile = sk_tiles + (long long)w * G + b;
+            sp.kt_begin = 0;
+            sp.kt_end = nkt;
+            ++w;
+            return true;
+        }
+        return false;
+    }
+};
+
 template <class T, bool TA>
 __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     hemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -195,20 +242,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     __syncthreads();
 
     const int nkt = (int)((p.K + BK - 1) / BK);
-    const long long it_begin = (long long)blockIdx.x * p.span;
-    const long long it_total = (long long)p.tiles_m * p.tiles_n * nkt;
-    const long long it_end = (it_begin + p.span < it_total) ? it_begin + p.span : it_total;
-    // next part of the span, walking down from it_hi
-    auto next_part = [&](long long it_hi) -> HemmSpan
-    {
-        HemmSpan sp;
-        sp.tile = (it_hi - 1) / nkt;
-        const long long first = sp.tile * nkt;
-        const long long lo = it_begin > first ? it_begin : first;
-        sp.kt_begin = (int)(lo - first);
-        sp.kt_end = (int)(it_hi - first);
-        return sp;
-    };
+    HemmWalk walk((long long)blockIdx.x, (long long)gridDim.x, p.span, p.sk_tiles, nkt, p.dp_waves, p.remap);
 
     if (warp >= CF::CONSUMER_WARPS)
     {
@@ -219,12 +253,10 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
             uint32_t it = 0;
-            for (long long hi = it_end; hi > it_begin;)
+            HemmSpan sp;
+            while (walk.next(sp))
             {
-                const HemmSpan sp = next_part(hi);
-                const long long rt = p.remap ? hemm_tile_remap(sp.tile, (long long)p.tiles_m * p.tiles_n, gridDim.x)
-                                             : sp.tile;
-                const int tn = (int)(rt % p.tiles_n), tm = (int)(rt / p.tiles_n);
+                const int tn = (int)(sp.tile % p.tiles_n), tm = (int)(sp.tile / p.tiles_n);
                 const int m0 = tm * BM, n0 = tn * BN;
                 for (int kt = sp.kt_begin; kt < sp.kt_end; ++kt, ++it)
                 {
@@ -244,7 +276,6 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
                     }
                     tma_load_2d(sb, &mapB, full, kt * BK * IMUL, n0);
                 }
-                hi -= (sp.kt_end - sp.kt_begin);
             }
         }
         return;
@@ -296,12 +327,10 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     }
 
     uint32_t it = 0;
-    for (long long hi = it_end; hi > it_begin;)
+    HemmSpan sp;
+    while (walk.next(sp))
     {
-        const HemmSpan sp = next_part(hi);
-        hi -= (sp.kt_end - sp.kt_begin);
-        const long long rt = p.remap ? hemm_tile_remap(sp.tile, (long long)p.tiles_m * p.tiles_n, gridDim.x) : sp.tile;
-        const int tn = (int)(rt % p.tiles_n), tm = (int)(rt / p.tiles_n);
+        const int tn = (int)(sp.tile % p.tiles_n), tm = (int)(sp.tile / p.tiles_n);
         const long long m0 = (long long)tm * BM, n0 = (long long)tn * BN;
 
         double accr[NJ][MI][2];
@@ -606,6 +635,12 @@ inline bool hemm_remap_disabled()
     const char* e = getenv("CHASE_B200_HEMM_REMAP");
     return e && atoi(e) == 0;
 }
+// CHASE_B200_HEMM_HYBRID=1: stream-K only for the ragged end, k-aligned whole-tile waves before it
+inline bool hemm_hybrid_enabled()
+{
+    const char* e = getenv("CHASE_B200_HEMM_HYBRID");
+    return e && atoi(e) != 0;
+}
 inline bool hemm_streamk_disabled()
 {
     static int v = -1;
@@ -615,6 +650,36 @@ inline bool hemm_streamk_disabled()
         v = (e && atoi(e) != 0) ? 1 : 0;
     }
     return v == 1;
+}
+
+// Launch geometry of the stream-K / hybrid schedule (shared with the host replay used by the tests)
+inline void hemm_schedule(long long ntiles, long long nkt, int sms, int& grid, long long& span, long long& sk_tiles,
+                          int& dp_waves, int& remap)
+{
+    remap = 0;
+    dp_waves = 0;
+    sk_tiles = ntiles;
+    if (ntiles >= sms && !hemm_streamk_disabled())
+    {
+        grid = sms;
+        remap = hemm_remap_disabled() ? 0 : 1;
+        // hybrid: stream-K over the last full wave + the ragged rest (between G and 2 G tiles, so span >= nkt still
+        // holds), whole-tile waves before it
+        if (hemm_hybrid_enabled() && ntiles >= 2 * (long long)sms)
+        {
+            dp_waves = (int)(ntiles / sms) - 1;
+            sk_tiles = ntiles - (long long)dp_waves * sms;
+        }
+        // equal spans of k-blocks, at most one incomplete tile at each end of a span
+        span = (sk_tiles * nkt + grid - 1) / grid;
+    }
+    else
+    {
+        // whole tiles per CTA (round-robin over tiles would need more than one span per CTA: use contiguous tiles)
+        grid = (int)(ntiles < sms ? ntiles : sms);
+        const long long tiles_per_cta = (ntiles + grid - 1) / grid;
+        span = tiles_per_cta * nkt;
+    }
 }
 
 template <class T>
@@ -679,21 +744,7 @@ inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Tr
     const long long ntiles = (long long)p.tiles_m * p.tiles_n;
     const long long nkt = (K + CF::BK - 1) / CF::BK;
     int grid;
-    p.remap = 0;
-    if (ntiles >= sms && !hemm_streamk_disabled())
-    {
-        // stream-K: equal spans of k-blocks, at most one incomplete tile at each end of a span
-        grid = sms;
-        p.span = (ntiles * nkt + grid - 1) / grid;
-        p.remap = hemm_remap_disabled() ? 0 : 1;
-    }
-    else
-    {
-        // whole tiles per CTA (round-robin over tiles would need more than one span per CTA: use contiguous tiles)
-        grid = (int)(ntiles < sms ? ntiles : sms);
-        const long long tiles_per_cta = (ntiles + grid - 1) / grid;
-        p.span = tiles_per_cta * nkt;
-    }
+    hemm_schedule(ntiles, nkt, sms, grid, p.span, p.sk_tiles, p.dp_waves, p.remap);
     HemmScratch* sc = hemm_scratch(dev, st, sms);
     if (!sc)
         return -1;

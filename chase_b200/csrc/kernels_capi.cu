@@ -1028,6 +1028,32 @@ extern "C" long long chase_b200_hemm_tile_remap(long long v, long long ntiles, l
     return hemm_tile_remap(v, ntiles, nctas);
 }
 
+// Host replay of the tile-part sequence CTA `cta` of the filter HEMM executes for ntiles x nkt k-blocks on `sms` SMs
+// (same HemmWalk / hemm_schedule code as the kernel): out[3 i .. 3 i + 2] = raster tile, kt_begin, kt_end.
+// Returns the number of parts (may exceed cap: only cap are written), or -1 if cta is outside the grid.
+extern "C" long long chase_b200_hemm_walk(long long ntiles, long long nkt, int sms, int cta, long long* out, long long cap)
+{
+    int grid = 0, dp_waves = 0, remap = 0;
+    long long span = 0, sk_tiles = 0;
+    hemm_schedule(ntiles, nkt, sms, grid, span, sk_tiles, dp_waves, remap);
+    if (cta < 0 || cta >= grid)
+        return -1;
+    HemmWalk walk(cta, grid, span, sk_tiles, (int)nkt, dp_waves, remap);
+    HemmSpan sp;
+    long long n = 0;
+    while (walk.next(sp))
+    {
+        if (n < cap)
+        {
+            out[3 * n] = sp.tile;
+            out[3 * n + 1] = sp.kt_begin;
+            out[3 * n + 2] = sp.kt_end;
+        }
+        ++n;
+    }
+    return n;
+}
+
 extern "C" int chase_b200_hemm_profile_enable(int on)
 {
     g_hprof.on = (on != 0);

@@ -179,6 +179,10 @@ extern "C"
     /* Virtual -> raster tile index of the stream-K filter HEMM (host copy of the device function, for tests):
        a bijection on [0, ntiles) that places the s-th tile of every CTA next to each other (L2 sharing of A). */
     long long chase_b200_hemm_tile_remap(long long v, long long ntiles, long long nctas);
+    /* Host replay of the work list of one CTA of the filter HEMM (stream-K / hybrid schedule; same code as the
+       kernel): out[3 i ..] = raster tile, first k-block, one-past-last k-block of part i.  Returns the number of
+       parts, -1 if cta is outside the grid.  For tests of coverage and of the head/tail hand-over order. */
+    long long chase_b200_hemm_walk(long long ntiles, long long nkt, int sms, int cta, long long* out, long long cap);
     /* Number of product kernels launched by this library so far (process-wide; bench.py's gpu_launches). */
     unsigned long long chase_b200_launch_count(void);
     /* Per-launch CUDA-event timing of the filter HEMM kernel on its launching stream.  enable(1) resets and

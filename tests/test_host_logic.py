@@ -59,3 +59,56 @@ def test_hemm_tile_remap_is_a_bijection_with_wave_locality():
     for s in range(T // G):
         block = sorted(f((c * T) // G + s, T, G) for c in range(G))
         assert block == list(range(s * G, (s + 1) * G))
+
+
+@pytest.mark.parametrize("hybrid", ["0", "1"])
+@pytest.mark.parametrize("ntiles,nkt", [(1727, 1250), (148, 40), (149, 7), (295, 64), (296, 64), (300, 3), (3454, 500),
+                                        (100, 10), (5, 33)])
+def test_hemm_schedule_covers_every_k_block_once_and_orders_the_handover(hybrid, ntiles, nkt):
+    """csrc/hemm_tma.cuh: HemmWalk / hemm_schedule replayed on the host for all 148 CTAs: every (tile, k-block) is
+    executed exactly once; a tile has at most two parts; the head part (low k, parked) belongs to CTA b and is the
+    FIRST part b executes, the tail part belongs to CTA b + 1 (deadlock-free hand-over); with the hybrid schedule all
+    CTAs enter the whole-tile phase after the same number of k-blocks (k-aligned waves)."""
+    import subprocess
+    import sys
+
+    code = f"""
+import ctypes, numpy as np, json
+from chase_b200 import lib
+f = lib().chase_b200_hemm_walk
+f.restype = ctypes.c_longlong
+f.argtypes = [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong]
+ntiles, nkt, sms = {ntiles}, {nkt}, 148
+cover = np.zeros((ntiles, nkt), dtype=np.int32)
+parts_of = {{}}
+lead = []
+for b in range(sms):
+    buf = np.zeros(3 * 64, dtype=np.int64)
+    n = f(ntiles, nkt, sms, b, buf.ctypes.data, 64)
+    if n < 0:
+        continue
+    assert n <= 64
+    ps = buf[:3 * n].reshape(n, 3)
+    sk = 0
+    for i, (t, k0, k1) in enumerate(ps):
+        assert 0 <= t < ntiles and 0 <= k0 < k1 <= nkt
+        cover[t, k0:k1] += 1
+        parts_of.setdefault(int(t), []).append((b, i, int(k0), int(k1), n))
+        if not (k0 == 0 and k1 == nkt):
+            sk = i + 1
+    whole = [i for i, (t, k0, k1) in enumerate(ps) if k0 == 0 and k1 == nkt]
+    lead.append(int(sum(k1 - k0 for (t, k0, k1) in ps[:sk])))
+assert cover.min() == 1 and cover.max() == 1
+for t, pl in parts_of.items():
+    assert len(pl) <= 2
+    if len(pl) == 2:
+        head = min(pl, key=lambda x: x[2]); tail = max(pl, key=lambda x: x[2])
+        assert head[2] == 0 and head[3] == tail[2] and tail[3] == nkt
+        assert tail[0] == head[0] + 1      # tail owner is the next CTA
+        assert head[1] == 0                # the head is the first thing its CTA does
+print(json.dumps(lead))
+"""
+    env = dict(os.environ, CHASE_B200_HEMM_HYBRID=hybrid)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, out.stderr[-2000:]
