@@ -635,11 +635,14 @@ inline bool hemm_remap_disabled()
     const char* e = getenv("CHASE_B200_HEMM_REMAP");
     return e && atoi(e) == 0;
 }
-// CHASE_B200_HEMM_HYBRID=1: stream-K only for the ragged end, k-aligned whole-tile waves before it
-inline bool hemm_hybrid_enabled()
+// Hybrid schedule: stream-K only for the ragged end, k-aligned whole-tile waves before it.  Default: on for
+// op(A) = A (measured at N=20000, k=1400: DRAM reads 8.4 GB instead of 42 GB at the same 31.4 ms; complex N=12000:
+// 45.9 vs 45.6 ms), off for op(A) = A^H until that variant has been measured too.  CHASE_B200_HEMM_HYBRID=0/1
+// forces it either way.
+inline bool hemm_hybrid_enabled(bool ta)
 {
     const char* e = getenv("CHASE_B200_HEMM_HYBRID");
-    return e && atoi(e) != 0;
+    return e ? atoi(e) != 0 : !ta;
 }
 inline bool hemm_streamk_disabled()
 {
@@ -653,8 +656,8 @@ inline bool hemm_streamk_disabled()
 }
 
 // Launch geometry of the stream-K / hybrid schedule (shared with the host replay used by the tests)
-inline void hemm_schedule(long long ntiles, long long nkt, int sms, int& grid, long long& span, long long& sk_tiles,
-                          int& dp_waves, int& remap)
+inline void hemm_schedule(long long ntiles, long long nkt, int sms, bool ta, int& grid, long long& span,
+                          long long& sk_tiles, int& dp_waves, int& remap)
 {
     remap = 0;
     dp_waves = 0;
@@ -665,7 +668,7 @@ inline void hemm_schedule(long long ntiles, long long nkt, int sms, int& grid, l
         remap = hemm_remap_disabled() ? 0 : 1;
         // hybrid: stream-K over the last full wave + the ragged rest (between G and 2 G tiles, so span >= nkt still
         // holds), whole-tile waves before it
-        if (hemm_hybrid_enabled() && ntiles >= 2 * (long long)sms)
+        if (hemm_hybrid_enabled(ta) && ntiles >= 2 * (long long)sms)
         {
             dp_waves = (int)(ntiles / sms) - 1;
             sk_tiles = ntiles - (long long)dp_waves * sms;
@@ -744,7 +747,7 @@ inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Tr
     const long long ntiles = (long long)p.tiles_m * p.tiles_n;
     const long long nkt = (K + CF::BK - 1) / CF::BK;
     int grid;
-    hemm_schedule(ntiles, nkt, sms, grid, p.span, p.sk_tiles, p.dp_waves, p.remap);
+    hemm_schedule(ntiles, nkt, sms, ta, grid, p.span, p.sk_tiles, p.dp_waves, p.remap);
     HemmScratch* sc = hemm_scratch(dev, st, sms);
     if (!sc)
         return -1;

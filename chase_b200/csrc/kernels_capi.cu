@@ -1035,7 +1035,7 @@ extern "C" long long chase_b200_hemm_walk(long long ntiles, long long nkt, int s
 {
     int grid = 0, dp_waves = 0, remap = 0;
     long long span = 0, sk_tiles = 0;
-    hemm_schedule(ntiles, nkt, sms, grid, span, sk_tiles, dp_waves, remap);
+    hemm_schedule(ntiles, nkt, sms, false, grid, span, sk_tiles, dp_waves, remap);
     if (cta < 0 || cta >= grid)
         return -1;
     HemmWalk walk(cta, grid, span, sk_tiles, (int)nkt, dp_waves, remap);

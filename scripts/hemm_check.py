@@ -23,9 +23,11 @@ for t, dt in (("d", torch.float64), ("z", torch.complex128)):
     C0 = torch.randn((kc, l2), dtype=dt, device="cuda")
     # column-major views: A is (nn x nn) with ld l2 -> reference in torch on the transposed storage
     ref = 0.5 * (B[:, :nn] @ A[:, :nn] - 1.0 * B[:, :nn]) - 0.25 * C0[:, :nn]  # (C^T = B^T A^T): rows = columns of C
-    for mode, env in (("plain", {"CHASE_B200_HEMM_REMAP": "0", "CHASE_B200_HEMM_HYBRID": "0"}),
+    for mode, env in (("default", {}), ("plain", {"CHASE_B200_HEMM_REMAP": "0", "CHASE_B200_HEMM_HYBRID": "0"}),
                       ("remap", {"CHASE_B200_HEMM_REMAP": "1", "CHASE_B200_HEMM_HYBRID": "0"}),
                       ("hybrid", {"CHASE_B200_HEMM_REMAP": "1", "CHASE_B200_HEMM_HYBRID": "1"})):
+        for key in ("CHASE_B200_HEMM_REMAP", "CHASE_B200_HEMM_HYBRID"):
+            os.environ.pop(key, None)
         os.environ.update(env)
         C = C0.clone()
         K.hemm(nn, kc, 0.5, A, l2, B, l2, -0.25, C, l2, 1.0)
