@@ -315,6 +315,17 @@ void with_active_config(F&& f)
         f(PCP::get().solver->GetConfig());
 }
 
+// keeps the matrix-object constructors of the backends (reference chase_gpu.hpp:195-267) compiled
+[[maybe_unused]] void* instantiate_matrix_constructors(chase::matrix::Matrix<double>* Hd,
+                                                       chase::matrix::PseudoHermitianMatrix<std::complex<double>>* Hz,
+                                                       double* Vd, std::complex<double>* Vz, double* r)
+{
+    using PH = chase::matrix::PseudoHermitianMatrix<std::complex<double>>;
+    if (Hd)
+        return new chase::Impl::ChASEGPU<double>(Hd->rows(), 1, 0, Hd, Vd, Hd->rows(), r);
+    return new chase::Impl::ChASEGPU<std::complex<double>, PH>(Hz->rows(), 1, 0, Hz, Vz, Hz->rows(), r);
+}
+
 size_t copy_out(const std::string& s, char* buf, size_t cap)
 {
     if (buf && cap > 0)

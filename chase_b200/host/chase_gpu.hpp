@@ -148,6 +148,11 @@ public:
                                       wide_scratch_bytes_);
         }
     }
+    // the reference's second constructor: H as a (host-backed) matrix object (chase_gpu.hpp:195-267)
+    ChASEGPU(std::size_t N, std::size_t nev, std::size_t nex, MatrixType* H, T* V1, std::size_t ldv, R* ritzv)
+        : ChASEGPU(N, nev, nex, check_matrix(H, N)->cpu_data(), H->cpu_ld(), V1, ldv, ritzv)
+    {
+    }
     ChASEGPU(const ChASEGPU&) = delete;
     ~ChASEGPU() override
     {
@@ -629,6 +634,12 @@ public:
     }
 
 private:
+    static MatrixType* check_matrix(MatrixType* H, std::size_t N)
+    {
+        if (H == nullptr || H->cpu_data() == nullptr || H->rows() != N || H->cols() != N)
+            throw std::invalid_argument("ChASEGPU: H must be an N x N matrix with a host buffer");
+        return H;
+    }
     static std::size_t roundup(std::size_t a, std::size_t b) { return (a + b - 1) / b * b; }
     template <class U>
     U* alloc(std::size_t n)

@@ -59,9 +59,11 @@ inline T getRandomT(F&& f)
     }
 }
 
-// Matrix-type tags selecting the problem class of a backend, named like the reference's containers
-// (linalg/matrix/matrix.hpp:1202 Matrix<T, GPU>, :1597 PseudoHermitianMatrix<T, GPU>).  Here they carry no storage: the backends own
-// their device buffers and take the caller's raw host pointers.
+// Matrix types selecting the problem class of a backend, named like the reference's containers
+// (linalg/matrix/matrix.hpp:1202 Matrix<T, GPU>, :1597 PseudoHermitianMatrix<T, GPU>).  Here they are views of the
+// caller's host buffer (rows, cols, leading dimension, pointer): the backends own their device storage.  They serve
+// as the MatrixType template argument and as the argument of the reference's second backend constructor
+// (Impl/chase_gpu/chase_gpu.hpp:195-267).
 namespace platform
 {
 struct CPU
@@ -74,16 +76,27 @@ struct GPU
 namespace matrix
 {
 template <class T, class Platform = chase::platform::GPU>
-struct Matrix
+class Matrix
 {
+public:
     using value_type = T;
     using platform_type = Platform;
+    Matrix() = default;
+    Matrix(std::size_t rows, std::size_t cols, std::size_t ld, T* host) : rows_(rows), cols_(cols), ld_(ld), data_(host) {}
+    std::size_t rows() const { return rows_; }
+    std::size_t cols() const { return cols_; }
+    std::size_t cpu_ld() const { return ld_; }
+    T* cpu_data() const { return data_; }
+
+private:
+    std::size_t rows_ = 0, cols_ = 0, ld_ = 0;
+    T* data_ = nullptr;
 };
 template <class T, class Platform = chase::platform::GPU>
-struct PseudoHermitianMatrix
+class PseudoHermitianMatrix : public Matrix<T, Platform>
 {
-    using value_type = T;
-    using platform_type = Platform;
+public:
+    using Matrix<T, Platform>::Matrix;
 };
 } // namespace matrix
 
