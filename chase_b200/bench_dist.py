@@ -22,10 +22,21 @@ def weak_n(gpus: int) -> int:
     return int(round(BASE[1] * np.sqrt(gpus) / 64.0)) * 64
 
 
-def lowrank_terms(N: int, cplx: bool):
-    """A = diag(lam) + sum_t coef[t] * X[:, t] Y[:, t]^H, identical to bench.make_matrix / oracle.dense_from_spectrum
-    before its final symmetrisation."""
+def sequence_spectrum(N: int, step: int, delta: float = 1e-4):
+    """Spectrum of problem `step` of a correlated sequence (BASELINE config C3): the uniform spectrum
+    with lambda_k <- lambda_k (1 + delta g_k) applied once per step (g ~ N(0,1), seeded per step); same eigenvectors,
+    spectrum known exactly.  step 0 = the unperturbed problem."""
     lam = 100.0 * (1e-4 + np.arange(N) * (1.0 - 1e-4) / N)
+    for t in range(1, step + 1):
+        lam = lam * (1.0 + delta * np.random.default_rng(1000 + t).standard_normal(N))
+    return lam
+
+
+def lowrank_terms(N: int, cplx: bool, lam=None):
+    """A = diag(lam) + sum_t coef[t] * X[:, t] Y[:, t]^H, identical to bench.make_matrix / oracle.dense_from_spectrum
+    before its final symmetrisation (lam: the reference generator's uniform spectrum unless given)."""
+    if lam is None:
+        lam = 100.0 * (1e-4 + np.arange(N) * (1.0 - 1e-4) / N)
     rng = np.random.default_rng(7)
     X, Y, coef = [], [], []
 
@@ -48,12 +59,12 @@ def lowrank_terms(N: int, cplx: bool):
     return lam, np.stack(X, 1), np.stack(Y, 1), np.array(coef)
 
 
-def local_block(N, gr, gc, cplx, device, transposed=False):
+def local_block(N, gr, gc, cplx, device, transposed=False, lam=None):
     """This rank's block A[gr, gc] as a torch tensor (m_loc, n_loc); transposed=True returns it as (n_loc, m_loc)
     row-major, i.e. the column-major m_loc x n_loc array the solver wants, without an extra copy."""
     import torch
 
-    lam, X, Y, coef = lowrank_terms(N, cplx)
+    lam, X, Y, coef = lowrank_terms(N, cplx, lam)
     dt = torch.complex128 if cplx else torch.float64
     Xl = torch.from_numpy(X[gr, :] * coef[None, :]).to(device).to(dt)
     Yl = torch.from_numpy(Y[gc, :]).to(device).to(dt)

@@ -8,6 +8,13 @@ block-cyclic block from 9 rank-one terms on its own GPU and hands it to the solv
 
     torchrun --nproc-per-node 8 scripts/run_dist.py --pseudo --type z --N 40000 --nev 500 --nex 200   # config C5
 
+    torchrun --nproc-per-node 4 scripts/run_dist.py --type z --N 60000 --nev 1000 --nex 300 --layout block --seq 5  # C3
+
+--seq k: a sequence of k correlated problems (same eigenvectors, spectrum perturbed by 1e-4 relative per step,
+chase_b200.bench_dist.sequence_spectrum): the first is solved from random vectors, the others re-use the previous
+eigenvectors and Ritz values (mode 'A'), the new local block being rebuilt and handed over on the device each time.
+--layout block: the reference's block distribution instead of block-cyclic.
+
 --pseudo: the pseudo-Hermitian (BSE) problem class through p?chase_init_pseudo_blockcyclic_ on the synthetic BSE matrix
 of chase_b200.bench_dist.bse_terms (spectrum +-lam known exactly; type z or c)."""
 import argparse
@@ -33,6 +40,9 @@ ap.add_argument("--nb", type=int, default=64)
 ap.add_argument("--solves", type=int, default=1)
 ap.add_argument("--out", default="")
 ap.add_argument("--pseudo", action="store_true")
+ap.add_argument("--seq", type=int, default=1)
+ap.add_argument("--perturb", type=float, default=1e-4)
+ap.add_argument("--layout", default="cyclic", choices=["cyclic", "block"])
 ap.add_argument("--tol", type=float, default=0.0)
 ap.add_argument("--deg", type=int, default=20)
 ap.add_argument("--lam-max", type=float, default=100.0, help="--pseudo: positive spectrum is uniform in [1, lam-max]")
@@ -46,6 +56,8 @@ world = cd.World()
 G = world.size
 r, c = cd.grid_dims(G)
 i, j = cd.grid_coords(r, c, "R", world.rank)
+if a.layout == "block":
+    a.nb = 0
 gr, gc = cd.global_indices(a.N, r, a.nb, i), cd.global_indices(a.N, c, a.nb, j)
 cplx = a.type in ("z", "c")
 dt = {"z": np.complex128, "c": np.complex64, "d": np.float64}[a.type]
@@ -61,18 +73,30 @@ else:
 solver.load_device_matrix(At.data_ptr(), len(gr))
 del At
 torch.cuda.empty_cache()
+if a.seq > 1 and a.pseudo:
+    raise SystemExit("--seq is implemented for Hermitian problems")
 import ctypes  # noqa: E402
 
 L.chase_b200_set_device_rng_(ctypes.byref(ctypes.c_int(1)))
 L.chase_set_upperb_scale_rate_(ctypes.byref(ctypes.c_float(a.upperb_scale)))
 L.chase_set_max_iter_(ctypes.byref(ctypes.c_int(a.max_iter)))
 out = []
-for s in range(a.solves):
+for s in range(a.solves * a.seq):
+    step = s % a.seq
+    if a.seq > 1 and s > 0:
+        # next problem of the sequence: same Q, perturbed spectrum; previous eigenpairs stay in solver.V / ritzv
+        lam_s = bd.sequence_spectrum(a.N, step, a.perturb)
+        At, lam = bd.local_block(a.N, gr, gc, cplx, f"cuda:{world.device}", transposed=True, lam=lam_s)
+        lam = np.sort(lam)
+        solver.load_device_matrix(At.data_ptr(), len(gr))
+        del At
+        torch.cuda.empty_cache()
     torch.cuda.synchronize()
     world.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = solver.solve(deg=a.deg, tol=tol, copy=False, trace=bool(os.environ.get("CHASE_B200_TRACE")))
+    res = solver.solve(deg=a.deg, tol=tol, copy=False, trace=bool(os.environ.get("CHASE_B200_TRACE")),
+                       mode="A" if (a.seq > 1 and step > 0) else "R")
     e1.record()
     torch.cuda.synchronize()
     secs = world.max(e0.elapsed_time(e1) * 1e-3)
@@ -80,8 +104,9 @@ for s in range(a.solves):
     st = res.stats
     es = np.dtype(dt).itemsize
     rec = dict(type=a.type, pseudo_hermitian=bool(a.pseudo), tol=tol, lam_max=a.lam_max if a.pseudo else None,
+               sequence_step=step if a.seq > 1 else None, mode="A" if (a.seq > 1 and step > 0) else "R",
                upperb_scale=a.upperb_scale, N=a.N, nev=a.nev, nex=a.nex, gpus=G,
-               grid=f"{r}x{c}", layout=f"block-cyclic {a.nb}",
+               grid=f"{r}x{c}", layout=f"block-cyclic {a.nb}" if a.nb else "block",
                time_to_solution_s=secs, iterations=res.iterations, filtered_vecs=res.filtered_vecs,
                filter_tflops_whole_job=st["gflop_filter"] / st["t_filter"] / 1e3,
                filter_tflops_per_gpu=st["gflop_filter"] / st["t_filter"] / 1e3 / G,

@@ -131,3 +131,23 @@ def test_world_size_2_gloo_plumbing():
         p.join(60)
         assert p.exitcode == 0
     assert all(all(v.values()) for _, v in res)
+
+
+def test_sequence_generator_has_the_stated_spectrum_and_fixed_eigenvectors():
+    """chase_b200.bench_dist.sequence_spectrum / local_block(lam=...): the correlated-sequence matrices of BASELINE
+    config C3 (scripts/run_dist.py --seq) keep Q and perturb the known spectrum by 1e-4 relative per step."""
+    from chase_b200 import bench_dist as bd
+
+    N = 200
+    idx = np.arange(N)
+    A0, lam0 = bd.local_block(N, idx, idx, True, "cpu")
+    lam2 = bd.sequence_spectrum(N, 2)
+    A2, lam = bd.local_block(N, idx, idx, True, "cpu", lam=lam2)
+    assert np.array_equal(lam, lam2) and np.array_equal(lam0, bd.sequence_spectrum(N, 0))
+    assert 0 < np.max(np.abs(lam2 / lam0 - 1)) < 1e-3
+    w, Q = np.linalg.eigh(A0.numpy())
+    assert np.max(np.abs(w - lam0)) < 1e-11
+    # same eigenvectors: Q^H A2 Q is diagonal with the perturbed spectrum
+    D = Q.conj().T @ A2.numpy() @ Q
+    assert np.max(np.abs(D - np.diag(np.diag(D)))) < 1e-10
+    assert np.max(np.abs(np.sort(np.diag(D).real) - np.sort(lam2))) < 1e-11
