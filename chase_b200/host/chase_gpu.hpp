@@ -338,7 +338,7 @@ public:
         int info = 1;
         if (disable == 1 && cond != R(1.0))
         {
-            // qr == 'H' / CHASE_DISABLE_CHOLQR=1: Householder QR (chase_gpu.hpp:836-857)
+            // qr == 'H' / CHASE_DISABLE_CHOLQR=1: Householder QR (chase_gpu.hpp:822-846)
             householder();
             info = 0;
             last_qr_ = "householder";
@@ -521,7 +521,7 @@ public:
         return is_sym_;
     }
     bool isSym() override { return !kPseudo; }
-    // S H Hermitian?  (reference: flip the lower half, checkSymmetryEasy, flip back; chase_gpu.hpp:474-487)
+    // S H Hermitian?  (reference: flip the lower half, checkSymmetryEasy, flip back; chase_gpu.hpp:482-500)
     bool checkPseudoHermicityEasy() override
     {
         if (N_ % 2 != 0)
@@ -581,7 +581,7 @@ public:
     }
 
     // Raw column-major binary matrix files, the reference's format (Matrix::readFromBinaryFile / saveToBinaryFile,
-    // linalg/matrix/matrix.hpp:276-352; ChASEGPU::loadProblemFromFile, chase_gpu.hpp:436-440): N*N elements, no
+    // linalg/matrix/matrix.hpp:276-352; ChASEGPU::loadProblemFromFile, chase_gpu.hpp:457-461): N*N elements, no
     // header.  The file lands in the caller's host H, which the next solve uploads.
     void loadProblemFromFile(const std::string& filename)
     {

@@ -22,7 +22,7 @@
 //
 // MatrixType = chase::matrix::PseudoHermitianMatrix<T, GPU> selects the pseudo-Hermitian (BSE) problem class on any
 // of the layouts (the reference: PseudoHermitianBlockBlockMatrix / PseudoHermitianBlockCyclicMatrix, block-block
-// multivectors only, pchase_gpu.hpp:903-945, 1068-1330): panels hold 2 (nev+nex) columns; H x is formed with the same
+// multivectors only, pchase_gpu.hpp:903-1030): panels hold 2 (nev+nex) columns; H x is formed with the same
 // two local products through H = S H^H S (S = sign flip of the rows whose global index is in the lower half);
 // K-conjugation exchanges the two halves of full-length copies (all-gather inside the grid column) instead of the
 // reference's pairwise send/recv (distMultiVector.hpp:1879-2060).
@@ -202,7 +202,7 @@ public:
                 CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)nc_, dV1_, (int64_t)ldv_, dV0_, (int64_t)ldv_, stream_));
             }
         }
-        if (random && kPseudo) // damp the lower (de-excitation) block: T(0.001), pchase_gpu.hpp:700-716
+        if (random && kPseudo) // damp the lower (de-excitation) block: T(0.001), pchase_gpu.hpp:668-690
             CB2_KCHECK(KK::scale_rows_map((int64_t)m_loc_, (int64_t)nc_, map_full2v_, (int64_t)(N_ / 2), dV1_,
                                           (int64_t)ldv_, (double)(R)0.001, stream_));
         CB2_KCHECK(KK::lacpy((int64_t)ldv_, (int64_t)nc_, dV1_, (int64_t)ldv_, dV2_, (int64_t)ldv_, stream_));
@@ -302,7 +302,7 @@ public:
         CB2_KCHECK(KK::lacpy((int64_t)m_loc_, (int64_t)locked_, dV1_, (int64_t)ldv_, dV2_, (int64_t)ldv_, stream_));
         if (kPseudo)
         {
-            // [L+ | active | L-] -> orthogonalise [S L+ | S L- | active] (pchase_gpu.hpp:1068-1120)
+            // [L+ | active | L-] -> orthogonalise [S L+ | S L- | active] (pchase_gpu.hpp:961-1030)
             const std::size_t act = nc_ - 2 * locked_;
             const int64_t m = (int64_t)m_loc_, ld = (int64_t)ldv_;
             CB2_KCHECK(KK::lacpy(m, (int64_t)locked_, dV1_ + (nc_ - locked_) * ldv_, ld, dV2_ + (nc_ - locked_) * ldv_, ld,
@@ -326,7 +326,7 @@ public:
         int info = 1;
         if (disable == 1 && cond != R(1.0))
         {
-            householder(); // qr == 'H' / CHASE_DISABLE_CHOLQR=1 (pchase_gpu.hpp:1142-1190)
+            householder(); // qr == 'H' / CHASE_DISABLE_CHOLQR=1 (pchase_gpu.hpp:1117-1192)
             info = 0;
             last_qr_ = "householder";
         }
@@ -349,7 +349,7 @@ public:
         }
         if (info != 0)
         {
-            householder(); // CholeskyQR broke down: Householder QR, as the reference (pchase_gpu.hpp:1254-1300)
+            householder(); // CholeskyQR broke down: Householder QR, as the reference (pchase_gpu.hpp:1455-1533)
             last_qr_ += "+householder";
         }
         qr_log_.push_back(last_qr_);
@@ -624,7 +624,7 @@ public:
 
     // Global matrix files (raw column-major N x N, the reference's format): every rank reads / writes the pieces of
     // its own local block at their global offsets (reference: MPI-IO darray views for block-cyclic matrices,
-    // linalg/distMatrix/distMatrix.hpp:3117-3196, per-rank seeks for block matrices).  All ranks of one node share the
+    // linalg/distMatrix/distMatrix.hpp:3117-3196; block matrices: MPI-IO subarray views, :2241-2330).  All ranks of one node share the
     // file; the caller synchronises the ranks between a write and a read.
     void loadProblemFromFile(const std::string& filename)
     {

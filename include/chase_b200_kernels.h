@@ -122,7 +122,7 @@ extern "C"
        conventions: R_jj real, sign -sign(Re x_j)), A <- R (upper triangle) and the reflectors.  ws: at least            \
        chase_b200_hhqr_ws_bytes(rows, n, sizeof(element)).  Replaces cusolverDnTgeqrf + cusolverDnTorgqr/ungqr of        \
        cuda::houseHoulderQR (reference linalg/internal/cuda/cholqr.hpp:524-556), the fallback of ChASEGPU::QR when       \
-       CholQR breaks down or qr == 'H' (Impl/chase_gpu/chase_gpu.hpp:836-919). */                                        \
+       CholQR breaks down or qr == 'H' (Impl/chase_gpu/chase_gpu.hpp:822-919). */                                        \
     int chase_b200_hhqr_##X(int64_t rows, int64_t n, void* A, int64_t lda, void* Q, int64_t ldq, void* ws,            \
                             size_t ws_bytes, void* stream);                                                           \
     /* X[0:nrows, 0:cols] *= a (X points at the first row to scale).  a = -1 on rows [N/2, N) is S X of the           \
