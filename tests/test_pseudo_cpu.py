@@ -116,6 +116,9 @@ XCHECK = [
     ("xcheck_d", ["--N", "256", "--nev", "24", "--nex", "16", "--deg", "16"]),
     ("xcheck_z", ["--N", "300", "--nev", "30", "--nex", "20"]),
     ("xcheck_d", ["--N", "300", "--nev", "30", "--nex", "10", "--opt", "0"]),
+    ("xcheck_s", ["--N", "256", "--nev", "24", "--nex", "16", "--deg", "16", "--tol", "1e-5"]),
+    ("xcheck_c", ["--N", "256", "--nev", "24", "--nex", "16", "--deg", "10", "--tol", "1e-5"]),
+    ("xcheck_z", ["--N", "400", "--nev", "40", "--nex", "20", "--maxiter", "3"]),
     ("xcheck_pz", ["--N", "200", "--nev", "20", "--nex", "20", "--numlanczos", "10", "--lanczositer", "40",
                    "--matrix", "file:" + os.path.join(BSE, "cdouble_random_BSE.bin")]),
     ("xcheck_pz", ["--N", "200", "--nev", "20", "--nex", "10",
