@@ -12,6 +12,7 @@
 #include "chase_gpu.hpp"
 #include "pchase_gpu.hpp"
 #include "performance.hpp"
+#include "tridiag_host.hpp"
 
 #include <complex>
 #include <cstring>
@@ -756,6 +757,12 @@ extern "C"
     CB2_IO_API(z, SZ, SZP, PZ, PZP)
     CB2_IO_API(c, SC, SCP, PC, PCP)
 #undef CB2_IO_API
+
+    // host tridiagonal eigensolver of the Lanczos step (exported for the CPU tests)
+    int chase_b200_tridiag_eig_host(int n, const double* d, const double* e, double* w, double* Z)
+    {
+        return chase::b200::tridiag_eig_host(n, d, e, w, Z);
+    }
 
     // ---- communicator bootstrap (include/chase_b200_comm.h) ------------------------------------------------
     int chase_b200_comm_unique_id(void* id_out)

@@ -33,6 +33,7 @@
 #include "dist_layout.hpp"
 #include "interface.hpp"
 #include "kernel_api.hpp"
+#include "tridiag_host.hpp"
 
 #include <cuda_runtime_api.h>
 
@@ -1028,8 +1029,6 @@ private:
     {
         flush_perm();
         resid_ready_ = false;
-        if (M > 48)
-            throw std::runtime_error("chase_b200: Lanczos with more than 48 steps is not supported yet");
         const int nv = (int)numvec, m = (int)M;
         ensure_lanczos_buffers(M, numvec);
         T* v0 = lan_v_;
@@ -1071,11 +1070,8 @@ private:
         }
         if (multi)
             full_to_v(v1, dV1_, numvec);
-        CB2_KCHECK(chase_b200_tridiag_eig(m, nv, lan_d_, lan_e_, m, lan_w_, lan_Z_, stream_));
-        std::vector<double> w(M * numvec), Z(M * M * numvec);
-        CB2_CHECK(cudaMemcpyAsync(w.data(), lan_w_, w.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-        CB2_CHECK(cudaMemcpyAsync(Z.data(), lan_Z_, Z.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-        CB2_CHECK(cudaStreamSynchronize(stream_));
+        std::vector<double> w, Z;
+        lanczos_tridiag_solve(M, numvec, w, Z);
         for (std::size_t i = 0; i < numvec; ++i)
             for (std::size_t k = 0; k < M; ++k)
             {
@@ -1086,6 +1082,30 @@ private:
         for (std::size_t q = 0; q < M * M; ++q)
             ritzV[q] = (R)Z[(numvec - 1) * M * M + q];
         *upperb = Theta[M - 1];
+    }
+
+    // Ritz pairs of the numvec Lanczos tridiagonals (d, e on the device): w[i M + k] ascending, Z[i M^2 + r + k M].
+    // Up to 48 steps on the device (one CTA per matrix); beyond that on the host like the reference (?stemr,
+    // cuda/lanczos.hpp:270-299).  Synchronises the stream.
+    void lanczos_tridiag_solve(std::size_t M, std::size_t numvec, std::vector<double>& w, std::vector<double>& Z)
+    {
+        w.resize(M * numvec);
+        Z.resize(M * M * numvec);
+        if (M <= 48)
+        {
+            CB2_KCHECK(chase_b200_tridiag_eig((int)M, (int)numvec, lan_d_, lan_e_, (int)M, lan_w_, lan_Z_, stream_));
+            CB2_CHECK(cudaMemcpyAsync(w.data(), lan_w_, w.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            CB2_CHECK(cudaMemcpyAsync(Z.data(), lan_Z_, Z.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            CB2_CHECK(cudaStreamSynchronize(stream_));
+            return;
+        }
+        std::vector<double> d(M * numvec), e(M * numvec);
+        CB2_CHECK(cudaMemcpyAsync(d.data(), lan_d_, d.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaMemcpyAsync(e.data(), lan_e_, e.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB2_CHECK(cudaStreamSynchronize(stream_));
+        for (std::size_t i = 0; i < numvec; ++i)
+            if (b200::tridiag_eig_host((int)M, d.data() + i * M, e.data() + i * M, w.data() + i * M, Z.data() + i * M * M))
+                throw std::runtime_error("chase_b200: the Lanczos tridiagonal eigensolver did not converge");
     }
 
     void ensure_lanczos_buffers(std::size_t M, std::size_t numvec)
@@ -1113,8 +1133,6 @@ private:
     {
         flush_perm();
         resid_ready_ = false;
-        if (M > 48)
-            throw std::runtime_error("chase_b200: Lanczos with more than 48 steps is not supported yet");
         const int nv = (int)numvec, m = (int)M;
         ensure_lanczos_buffers(M, numvec);
         T* v0 = lan_v_;
@@ -1148,12 +1166,9 @@ private:
         }
         if (multi)
             full_to_v(v1, dV1_, numvec);
-        CB2_KCHECK(chase_b200_tridiag_eig(m, nv, lan_d_, lan_e_, m, lan_w_, lan_Z_, stream_));
-        std::vector<double> w(M * numvec), Z(M * M * numvec), rb(numvec);
-        CB2_CHECK(cudaMemcpyAsync(w.data(), lan_w_, w.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-        CB2_CHECK(cudaMemcpyAsync(Z.data(), lan_Z_, Z.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        std::vector<double> w, Z, rb(numvec);
         CB2_CHECK(cudaMemcpyAsync(rb.data(), lan_rb_, rb.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-        CB2_CHECK(cudaStreamSynchronize(stream_));
+        lanczos_tridiag_solve(M, numvec, w, Z);
         for (std::size_t i = 0; i < numvec; ++i)
             for (std::size_t k = 0; k < M; ++k)
             {

@@ -185,6 +185,10 @@ extern "C"
     void chase_b200_start_vectors_c(int64_t N, int64_t m, CHASE_B200_CF* V, int64_t ldv);
     /* message of the last failed init/solve ("" if none); stats[15] is 1 after a failed solve */
     size_t chase_b200_last_error_copy_(char* buf, size_t cap);
+    /* Symmetric tridiagonal eigen-decomposition on the host (implicit QL; w ascending, Z n x n column-major): what the
+       Lanczos bound estimation uses beyond the on-device solver's 48 steps (reference: host LAPACK ?stemr,
+       linalg/internal/cuda/lanczos.hpp:270-299).  Returns 0 or the 1-based index of a non-converged eigenvalue. */
+    int chase_b200_tridiag_eig_host(int n, const double* d, const double* e, double* w, double* Z);
     int chase_b200_device_sync(void);
     /* flag != 0: subsequent solves do NOT re-upload the host matrix H when a copy from an earlier solve is already
        on the device (default 0 = the reference's behaviour: H is re-read at every solve, chase_gpu.hpp:536) */

@@ -112,3 +112,32 @@ print(json.dumps(lead))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 49, 64, 120])
+def test_host_tridiagonal_eigensolver_matches_lapack(n):
+    """host/tridiag_host.hpp (Lanczos with more than 48 steps; the reference uses LAPACK ?stemr on the host,
+    cuda/lanczos.hpp:270-299): eigenvalues ascending, orthonormal eigenvectors, T Z = Z diag(w)."""
+    import scipy.linalg as sla
+
+    from chase_b200 import lib
+
+    rng = np.random.default_rng(n)
+    d = rng.standard_normal(n)
+    e = np.abs(rng.standard_normal(max(n - 1, 1))) + 0.1
+    w = np.zeros(n)
+    Z = np.zeros((n, n), order="F")
+    f = lib().chase_b200_tridiag_eig_host
+    rc = f(ctypes.c_int(n), d.ctypes.data_as(ctypes.c_void_p), e.ctypes.data_as(ctypes.c_void_p),
+           w.ctypes.data_as(ctypes.c_void_p), Z.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    T = np.diag(d) + (np.diag(e[: n - 1], 1) + np.diag(e[: n - 1], -1) if n > 1 else 0)
+    wr = np.linalg.eigvalsh(T) if n > 1 else d.copy()
+    scale = max(np.abs(wr).max(), 1.0)
+    assert np.all(np.diff(w) >= 0)
+    assert np.max(np.abs(w - wr)) < 1e-13 * scale * n
+    assert np.linalg.norm(Z.T @ Z - np.eye(n)) < 1e-12 * n
+    assert np.linalg.norm(T @ Z - Z * w) < 1e-12 * scale * n
+    if n > 1:
+        wl, Zl = sla.eigh_tridiagonal(d, e[: n - 1])
+        assert np.max(np.abs(np.abs(Z[0]) - np.abs(Zl[0]))) < 1e-9  # the DoS weights |z_0k|^2 agree
