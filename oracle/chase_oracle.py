@@ -257,6 +257,12 @@ class OracleBackend:
         if not dbl:
             # QR_DOUBLE_PRECISION only affects the Householder fallback on the CPU backend
             pass
+        if getattr(self, "disable_cholqr", False) and cond != 1.0:
+            # CHASE_DISABLE_CHOLQR=1 / qr == 'H': Householder QR in every iteration (chase_cpu.hpp:670-690)
+            householder_qr(work)
+            self.qr_variants.append("householder")
+            self.V1[:, : self.locked] = self.V2[:, : self.locked]
+            return
         if cond > upper:
             info = shifted_cholqr2(work)
             self.qr_variants.append("shifted2")

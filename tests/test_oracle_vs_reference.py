@@ -65,3 +65,26 @@ def test_start_vectors_match_libstdcxx_stream():
     s = co.mt_normal(1337, 48)
     assert np.array_equal(z.T.reshape(-1).imag, s[0::2])
     assert np.array_equal(z.T.reshape(-1).real, s[1::2])
+
+
+@pytest.mark.parametrize("name", ["hhqr_clement_d_N300", "hhqr_clement_z_N256"])
+def test_oracle_with_householder_qr_matches_reference_trace(name):
+    """Goldens produced with CHASE_DISABLE_CHOLQR=1 (Householder QR in every iteration, chase_cpu.hpp:670-690)."""
+    g = load(name)
+    p = g["problems"][0]
+    ref = parse_trace(p["trace"])
+    cfg = co.Config.for_dtype(DT[g["type"]])
+    cfg.tol, cfg.deg, cfg.opt = g["tol"], g["deg"], bool(g["opt"])
+    H = np.asfortranarray(_matrix(g).copy())
+    be = co.OracleBackend(H, g["nev"], g["nex"])
+    be.disable_cholqr = True
+    tr = co.solve(be, cfg)
+    hemm, qr, locks = _oracle_trace(tr)
+    assert tr.iterations == p["iterations"]
+    assert tr.filtered_vecs == p["filtered_vecs"]
+    assert hemm == [(b, o) for (b, o, _, _) in ref["hemm"]]
+    assert locks == ref["locks"]
+    assert be.qr_variants[0] == "chol1" and set(be.qr_variants[1:]) == {"householder"}
+    nev = g["nev"]
+    refv = np.array(p["ritzv"][:nev])
+    assert np.max(np.abs(be.ritzv[:nev] - refv) / np.abs(refv)) < 1e-10
