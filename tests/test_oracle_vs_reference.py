@@ -88,3 +88,32 @@ def test_oracle_with_householder_qr_matches_reference_trace(name):
     nev = g["nev"]
     refv = np.array(p["ritzv"][:nev])
     assert np.max(np.abs(be.ritzv[:nev] - refv) / np.abs(refv)) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["seq_clement_d_N400", "seq_clement_z_N400"])
+def test_oracle_sequence_with_approximate_start_matches_reference_trace(name):
+    """tests/noinput.cpp-style sequence (oracle/ref_driver.cpp --seq 3): problem 0 from random vectors, the following
+    ones perturbed element-wise and solved in mode 'A' from the previous eigenvectors / Ritz values."""
+    g = load(name)
+    dt = DT[g["type"]]
+    N, nev, nex = g["N"], g["nev"], g["nex"]
+    H = np.asfortranarray(co.clement(N, dt))
+    be = co.OracleBackend(H, nev, nex)
+    nseq = len(g["problems"])
+    stream = co.mt_normal(1337, (2 if g["type"] == "z" else 1) * nseq * N * N)
+    pos = 0
+    for idx, p in enumerate(g["problems"]):
+        ref = parse_trace(p["trace"])
+        cfg = co.Config.for_dtype(dt)
+        cfg.tol, cfg.deg, cfg.opt, cfg.approx = g["tol"], g["deg"], bool(g["opt"]), idx > 0
+        be.trace = co.Trace()
+        tr = co.solve(be, cfg)
+        hemm, qr, locks = _oracle_trace(tr)
+        assert tr.iterations == p["iterations"], idx
+        assert tr.filtered_vecs == p["filtered_vecs"], idx
+        assert hemm == [(b, o) for (b, o, _, _) in ref["hemm"]], idx
+        assert locks == ref["locks"], idx
+        refv = np.array(p["ritzv"][:nev])
+        assert np.max(np.abs(be.ritzv[:nev] - refv) / np.abs(refv)) < 1e-10
+        if idx + 1 < nseq:
+            pos += co.perturb_hermitian(be.H, stream[pos:], 1e-4)
