@@ -157,7 +157,7 @@ def run_reference_gpu(workload):
     out = f"/tmp/chase_refgpu_{os.getpid()}.json"
     try:
         subprocess.run([exe, "--N", str(N), "--nev", str(nev), "--nex", str(nex), "--matrix", "uniform_dense", "--out",
-                        out], env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=900)
+                        out], env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=300)
         r = json.load(open(out))["problems"][0]
         os.unlink(out)
     except Exception as e:  # noqa: BLE001
