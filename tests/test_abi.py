@@ -79,3 +79,13 @@ def test_solver_refuses_to_run_without_gpu():
     out = subprocess.run(["python", "-c", code], cwd=ROOT, capture_output=True, text=True)
     # a C++ exception crossing the C ABI terminates the process; either way it must not succeed silently
     assert "RAISED" in out.stdout or out.returncode != 0
+
+
+def test_every_function_of_the_reference_c_interface_is_exported(native):
+    """Drop-in check: all 94 functions the reference declares in interface/chase_c_interface.h (names recorded in
+    tests/golden/reference_c_symbols.txt) exist in libchase_b200.so."""
+    path = os.path.join(ROOT, "tests", "golden", "reference_c_symbols.txt")
+    names = [ln.strip() for ln in open(path) if ln.strip() and not ln.startswith("#")]
+    assert len(names) >= 90
+    missing = [n for n in names if not hasattr(native, n)]
+    assert not missing, missing
