@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the non-headline arms (weak, complex_fixed)")
+    ap.add_argument("--gpu-ref-repeats", type=int, default=3, help="timed solves of the same-box reference GPU backend")
     ap.add_argument("--ref-n", type=int, default=0, help="override the bounded-sample N of the CPU reference arm")
     ap.add_argument("--profile", action="store_true",
                     help="one warm solve + one profiled solve only (for `ncu`: no e2e, no CPU baseline)")
@@ -107,23 +109,25 @@ class Clocks:
 # --------------------------------------------------------------------------------------------------------------
 # reference CPU arm (oracle/_ref: the unmodified reference ChASECPU built from /root/reference by oracle/Makefile)
 # --------------------------------------------------------------------------------------------------------------
-def ref_sample_shape(workload, cores, override=0):
+def ref_sample_shape(workload, cores, override=0, budget_s=30.0):
+    """Bounded sample of the workload for the CPU solver: same generator, same nev/N and nex/N, N chosen so that one
+    solve takes about `budget_s` seconds (measured: real double N=6000 -> 12.5 s on 16 cores; time grows like N^3 at
+    fixed nev/N).  The full-size C2 run of the same binary is recorded in BASELINE.md / baseline/oracle_logs."""
     t, N, nev, nex = WORKLOADS[workload]
     if override:
         n = override
     else:
-        # ~10-30 s of CPU work: filter FLOPs grow like N^3 at fixed nev/N (971 GFLOP at N=4000, real double)
-        n = 4000 if cores <= 8 else (6000 if cores <= 32 else 8000)
-        if t == "z":
-            n = n * 5 // 8
+        t6000 = 12.5 * 16.0 / max(min(cores, 16), 1) * (4.0 if t == "z" else 1.0)
+        n = int(6000.0 * (budget_s / t6000) ** (1.0 / 3.0)) // 500 * 500
+        n = max(n, 2000)
     n = min(n, N)
     return t, n, max(nev * n // N, 4), max(nex * n // N, 4)
 
 
-def run_reference_cpu(workload, override=0):
+def run_reference_cpu(workload, override=0, budget_s=30.0):
     """One solve of the bounded sample with the reference CPU solver on all host cores -> dict."""
     cores = os.cpu_count() or 1
-    t, n, nev, nex = ref_sample_shape(workload, cores, override)
+    t, n, nev, nex = ref_sample_shape(workload, cores, override, budget_s)
     exe = os.path.join(ROOT, "oracle", "_ref", f"chase_ref_cpu_{t}")
     if not os.path.exists(exe):
         return {"error": f"{exe} not built (oracle/Makefile ref needs /root/reference)"}
@@ -145,33 +149,54 @@ def run_reference_cpu(workload, override=0):
             "tflops_per_solve": r["gflop_filter"] / t_all / 1e3, "tflops_filter_phase": r["gflop_filter"] / r["timings"]["Filter"] / 1e3}
 
 
-def run_reference_gpu(workload):
-    """One full-size solve with the reference's own single-GPU backend (separate process, same GPU) -> dict."""
+def run_reference_gpu(workload, repeats=3):
+    """The reference's own single-GPU backend (separate process, same GPU) on the FULL workload: one warm-up solve and
+    `repeats` timed solves of the same problem in ONE process (fresh cuRAND start vectors each), median and spread
+    reported.  BLAS threads pinned so the host-side phases (stemr, the driver's matrix generation) are reproducible."""
     t, N, nev, nex = WORKLOADS[workload]
     exe = os.path.join(ROOT, "oracle", "_ref", f"chase_ref_gpu_{t}")
     if not os.path.exists(exe):
         return {"unavailable": f"{exe} not built (make -C oracle refgpu needs /root/reference)"}
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = OB + ":/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
-    env["OPENBLAS_NUM_THREADS"] = env["OMP_NUM_THREADS"] = str(min(os.cpu_count() or 1, 128))
+    threads = min(os.cpu_count() or 1, 16)
+    env["OPENBLAS_NUM_THREADS"] = env["OMP_NUM_THREADS"] = str(threads)
     out = f"/tmp/chase_refgpu_{os.getpid()}.json"
     try:
-        subprocess.run([exe, "--N", str(N), "--nev", str(nev), "--nex", str(nex), "--matrix", "uniform_dense", "--out",
-                        out], env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=300)
-        r = json.load(open(out))["problems"][0]
+        subprocess.run([exe, "--N", str(N), "--nev", str(nev), "--nex", str(nex), "--matrix", "uniform_dense", "--repeat",
+                        str(repeats + 1), "--out", out], env=env, check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.PIPE, timeout=600)
+        ps = json.load(open(out))["problems"]
         os.unlink(out)
     except Exception as e:  # noqa: BLE001
         err = getattr(e, "stderr", b"") or b""
         return {"unavailable": f"{type(e).__name__}: {str(e)[:200]} {err[-300:].decode(errors='replace')}"}
-    tm = r["timings"]
+    warm, timed = ps[0], ps[1:]
+    alls = sorted(r["timings"]["All"] for r in timed)
+    med = timed[[r["timings"]["All"] for r in timed].index(alls[len(alls) // 2])]
+    tm = med["timings"]
     return {"impl": "reference ChASEGPU (cuBLAS / cuSOLVER / cuRAND), unmodified, same GPU, host buffers",
             "workload": f"{t} N={N} nev={nev} nex={nex} uniform spectrum, dense (driver's own reflectors)",
-            "time_to_solution_s": tm["All"], "iterations": r["iterations"], "filtered_vecs": r["filtered_vecs"],
-            "value": r["gflop_filter"] / tm["All"] / 1e3, "unit": "TFLOP/s",
-            "filter_phase_tflops": r["gflop_filter"] / tm["Filter"] / 1e3,
+            "protocol": f"one process: 1 warm-up solve + {len(timed)} timed solves, median reported; "
+                        f"OPENBLAS/OMP threads = {threads}",
+            "time_to_solution_s": tm["All"], "time_to_solution_all_s": [r["timings"]["All"] for r in timed],
+            "time_to_solution_min_s": alls[0], "time_to_solution_max_s": alls[-1],
+            "warmup_solve_s": warm["timings"]["All"],
+            "iterations": med["iterations"], "filtered_vecs": med["filtered_vecs"],
+            "value": med["gflop_filter"] / tm["All"] / 1e3, "unit": "TFLOP/s",
+            "filter_phase_tflops": med["gflop_filter"] / tm["Filter"] / 1e3,
             "phases_s": {k.lower(): tm[k] for k in ("InitVecs", "Lanczos", "Filter", "QR", "RR", "Resid")},
-            "max_resid": max(r["resid"][:nev]),
+            "max_resid": max(med["resid"][:nev]),
             "note": "start vectors from cuRAND, so the iteration count may differ from the parity-mode runs"}
+
+
+def hemm_traffic(key):
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of an ncu capture,
+    committed under profiles/ and indexed by profiles/hemm_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "hemm_traffic.json"))).get(key)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def sample_text(r):
@@ -184,9 +209,11 @@ def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the whole run (1 warm-up + K steps) is sized to ~5 minutes: every step solves the same bounded sample
+    budget = min(max(300.0 / (max(a.steps, 1) + 1), 5.0), 120.0)
     for _ in range(min(a.warmup, 1)):  # one untimed warm-up is enough for a CPU solver (page-in, thread pool)
-        run_reference_cpu(a.workload, a.ref_n)
-    rs = [run_reference_cpu(a.workload, a.ref_n) for _ in range(max(a.steps, 1))]
+        run_reference_cpu(a.workload, a.ref_n, budget)
+    rs = [run_reference_cpu(a.workload, a.ref_n, budget) for _ in range(max(a.steps, 1))]
     if "error" in rs[0]:
         print(json.dumps({"impl": "reference", "unavailable": rs[0]["error"]}))
         return
@@ -331,26 +358,22 @@ def ours(a):
     # ---- e2e: the reference C interface on host buffers ----------------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        flag("chase_b200_set_device_rng_", 0)
+        flag("chase_b200_set_device_rng_", 1)
         flag("chase_b200_set_matrix_resident_", 0)
         solver.solve(deg=20, tol=tol, copy=False)
         rs2, secs2, _ = timed(a.steps)
         rel = max(rel, max(check(r) for r in rs2))
         es = H.itemsize
         e2e = {"value": sum(r.stats["gflop_filter"] for r in rs2) * 1e9 / secs2 / 1e12, "unit": "TFLOP/s",
-               "h2d_bytes_per_step": N * N * es + N * m * es, "d2h_bytes_per_step": N * m * es + 2 * m * 8,
+               "h2d_bytes_per_step": N * N * es, "d2h_bytes_per_step": N * m * es + 2 * m * 8,
                "time_to_solution_s": secs2 / a.steps, "iterations": rs2[-1].iterations,
                "filtered_vecs": rs2[-1].filtered_vecs,
-               "start_vectors": "reference CPU stream (mt19937(1337)+normal; generated on the host at the first solve, "
-                                "kept on the device afterwards)"}
+               "start_vectors": "device Philox RNG, regenerated inside every timed step (the reference GPU backend "
+                                "regenerates with cuRAND every solve); nothing is cached between steps"}
     solver.finalize()
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "hemm_traffic.json"))).get(a.workload)
-    except Exception:
-        pass
+    traffic = hemm_traffic(a.workload)
     achieved = hp[2] / (hp[1] * 1e-3) / 1e12 if hp[1] > 0 else None
     roofline = {"bound": "tensor", "kernel": "hemm_tma_kernel (FP64 DMMA, TMA-fed)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
@@ -364,7 +387,7 @@ def ours(a):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64" if t == "d" else "c128", "data": "synthetic",
         "config": {"workload": f"{a.workload}: {t} N={N} nev={nev} nex={nex} uniform spectrum, dense Q diag Q^H, tol 1e-10 deg 20 opt",
                    "l2": "inputs larger than L2 (A is %.1f GB)" % (N * N * H.itemsize / 1e9),
-                   "start_vectors": "device Philox RNG (value) / reference CPU stream (e2e)"},
+                   "start_vectors": "device Philox RNG, regenerated every solve (value and e2e)"},
         "time_to_solution_s": secs / a.steps, "iterations": rs[-1].iterations, "filtered_vecs": rs[-1].filtered_vecs,
         "filter_phase_tflops": st["gflop_filter"] / st["t_filter"] / 1e3 if st["t_filter"] > 0 else None,
         "phases_s": {k[2:]: st[k] for k in ("t_all", "t_initvecs", "t_lanczos", "t_filter", "t_qr", "t_rr", "t_resid")},
@@ -379,7 +402,20 @@ def ours(a):
                                     "kind": "reference", "sample": sample_text(r),
                                     "filter_phase_tflops": r["tflops_filter_phase"], "host_cores": os.cpu_count()}
     if not a.no_gpu_reference:
-        line["gpu_reference"] = run_reference_gpu(a.workload)
+        g = run_reference_gpu(a.workload, a.gpu_ref_repeats)
+        line["gpu_reference"] = g
+        if e2e and "time_to_solution_s" in g:
+            # same box, same workload, host buffers on both sides: the like-for-like speed-up of the drop-in
+            line["e2e_vs_gpu_reference"] = g["time_to_solution_s"] / e2e["time_to_solution_s"]
+            line["filter_vs_gpu_reference"] = g["phases_s"]["filter"] / st["t_filter"]
+    if not a.no_extras and a.workload == "c2":
+        # the fixed complex problem of the multi-GPU arm, on the 1x1 grid of the distributed backend
+        from chase_b200 import bench_dist
+        from chase_b200 import dist as cd
+
+        world = cd.World(0, 1, 0)
+        line["complex_fixed"] = bench_dist.extra_arm(world, "z", 24000, 1000, 400, 64, 2, "fixed complex problem")
+        world.close()
     print(json.dumps(line))
 
 

@@ -1,9 +1,9 @@
 """Multi-GPU arm of bench.py (one rank per GPU under torchrun).
 
-Weak scaling of BASELINE config C2 over an r x c grid (1x1, 2x1, 2x2, 4x2): nev = 1000, nex = 400 fixed, N grows like
-sqrt(#GPUs) so that every GPU keeps a 3.2 GB block of A and the same filter work per call
-(N = 20000, 28288, 40000, 56576), block-cyclic layout with 64 x 64 blocks as in the reference's examples
-(examples/1_hello_world/1_hello_world.cpp:102).  The matrix is the same dense uniform-spectrum generator as the
+Headline: STRONG scaling of BASELINE config C2 (real double N = 20000, nev = 1000, nex = 400: the problem of the 1-GPU
+line, unchanged) over an r x c grid (2x1, 2x2, 4x2), block-cyclic layout with 64 x 64 blocks as in the reference's
+examples (examples/1_hello_world/1_hello_world.cpp:102).  Extra keys: `weak` = the round-1 arm (N grows like sqrt(#GPUs)
+so that every GPU keeps a 3.2 GB block: N = 28288, 40000, 56576) and `complex_fixed` (z N = 24000, same at every G).  The matrix is the same dense uniform-spectrum generator as the
 single-GPU arm, A = Q diag(lambda) Q^T with 3 Householder reflectors, written as diag + 9 rank-one terms so that every
 rank builds its own block on its own GPU without ever holding N^2 numbers.
 """
@@ -84,7 +84,63 @@ def local_block(N, gr, gc, cplx, device, transposed=False, lam=None):
     return A, lam
 
 
+def _flag(L, name, v):
+    getattr(L, name)(ctypes.byref(ctypes.c_int(v)))
+
+
+def extra_arm(world, t, N, nev, nex, nb, solves, label):
+    """One fixed problem solved `solves` times after one warm-up, matrix built per block on the GPUs and handed over on
+    the device, device RNG start vectors: an extra (non-headline) measurement reported under its own key."""
+    import torch
+
+    import chase_b200
+    from chase_b200 import dist as cd
+
+    L = chase_b200.lib()
+    G = world.size
+    r, c = cd.grid_dims(G)
+    i, j = cd.grid_coords(r, c, "R", world.rank)
+    gr, gc = cd.global_indices(N, r, nb, i), cd.global_indices(N, c, nb, j)
+    cplx = t == "z"
+    dt = np.complex128 if cplx else np.float64
+    solver = cd.PChASE(world, N, nev, nex, dt, grid=(r, c), major="R", mb=nb, nb=nb)
+    At, lam = local_block(N, gr, gc, cplx, f"cuda:{world.device}", transposed=True)
+    solver.load_device_matrix(At.data_ptr(), len(gr))
+    del At
+    torch.cuda.empty_cache()
+    _flag(L, "chase_b200_set_device_rng_", 1)
+    _flag(L, "chase_b200_set_matrix_resident_", 1)
+    solver.solve(deg=20, tol=1e-10, copy=False)  # warm-up
+    torch.cuda.synchronize()
+    L.chase_b200_device_sync()
+    world.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rs = [solver.solve(deg=20, tol=1e-10, copy=False) for _ in range(solves)]
+    e1.record()
+    torch.cuda.synchronize()
+    L.chase_b200_device_sync()
+    world.barrier()
+    secs = world.max(e0.elapsed_time(e1) * 1e-3)
+    rel = max(float(np.max(np.abs(x.ritzv[:nev] - lam[:nev]) / lam[:nev])) for x in rs)
+    assert rel < 1e-10, f"{label}: eigenvalues off: {rel}"
+    st = rs[-1].stats
+    solver.finalize()
+    _flag(L, "chase_b200_set_matrix_resident_", 0)
+    return {"workload": f"{label}: {t} N={N} nev={nev} nex={nex} uniform spectrum, dense Q diag Q^H, {r}x{c} grid, "
+                        f"block-cyclic {nb}", "solves": solves, "warmup": 1,
+            "value": sum(x.stats["gflop_filter"] for x in rs) * 1e9 / secs / 1e12, "unit": "TFLOP/s",
+            "time_to_solution_s": secs / solves, "iterations": rs[-1].iterations,
+            "filtered_vecs": rs[-1].filtered_vecs,
+            "filter_phase_tflops": st["gflop_filter"] / st["t_filter"] / 1e3 if st["t_filter"] > 0 else None,
+            "phases_s": {k[2:]: st[k] for k in ("t_all", "t_initvecs", "t_lanczos", "t_filter", "t_qr", "t_rr", "t_resid")},
+            "max_rel_eig_err": rel}
+
+
 def run(a):
+    """STRONG scaling of BASELINE config C2 (the workload of the 1-GPU line, N = 20000 fixed) over the r x c grid;
+    extra keys: `weak` (N = 20000 sqrt(G), the round-1 arm) and `complex_fixed` (z N = 24000, nev = 1000, nex = 400,
+    the same problem at every G)."""
     import torch
     import torch.distributed as tdist
 
@@ -100,13 +156,12 @@ def run(a):
                "--master-addr", "127.0.0.1", "--master-port", "29533"] + sys.argv
         raise SystemExit(subprocess.call(cmd))
 
-    from bench import Clocks, run_reference_cpu, sample_text  # noqa: E402 (bench.py is on sys.path)
+    from bench import Clocks, hemm_traffic  # noqa: E402 (bench.py is on sys.path)
 
     L = chase_b200.lib()
     world = cd.World()
     rank, G = world.rank, world.size
-    t, _, nev, nex = BASE
-    N = weak_n(G)
+    t, N, nev, nex = BASE
     m = nev + nex
     r, c = cd.grid_dims(G)
     nb = 64
@@ -122,9 +177,6 @@ def run(a):
     H, V = Hh.numpy().T, Vh.numpy().T
 
     peak = max(L.chase_b200_dmma_peak(40000, None) for _ in range(3)) / 1e12
-
-    def flag(name, v):
-        getattr(L, name)(ctypes.byref(ctypes.c_int(v)))
 
     solver = cd.PChASE(world, N, nev, nex, H, grid=(r, c), major="R", mb=nb, nb=nb, V_loc=V)
     tol = 1e-10
@@ -151,10 +203,10 @@ def run(a):
         return rs, world.max(e0.elapsed_time(e1) * 1e-3), L.chase_b200_launch_count() - l0
 
     # ---- value: local blocks resident in HBM, device RNG ----------------------------------------------------
-    flag("chase_b200_set_device_rng_", 1)
-    flag("chase_b200_set_matrix_resident_", 0)
+    _flag(L, "chase_b200_set_device_rng_", 1)
+    _flag(L, "chase_b200_set_matrix_resident_", 0)
     solver.solve(deg=20, tol=tol, copy=False)
-    flag("chase_b200_set_matrix_resident_", 1)
+    _flag(L, "chase_b200_set_matrix_resident_", 1)
     for _ in range(max(a.warmup - 1, 0)):
         solver.solve(deg=20, tol=tol, copy=False)
     L.chase_b200_hemm_profile_enable(1)
@@ -172,44 +224,58 @@ def run(a):
     st = rs[-1].stats
     kern_tf = hp[2] / (hp[1] * 1e-3) / 1e12 if hp[1] > 0 else 0.0
     kern_tf_min = -world.max(-kern_tf)
+    # per-phase seconds: max over ranks (the serial fraction of the strong-scaling curve is read from these)
+    phases = {k[2:]: world.max(st[k]) for k in ("t_all", "t_initvecs", "t_lanczos", "t_filter", "t_qr", "t_rr", "t_resid")}
 
     # ---- e2e: host buffers through p?chase_ ---------------------------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        flag("chase_b200_set_device_rng_", 0)
-        flag("chase_b200_set_matrix_resident_", 0)
+        _flag(L, "chase_b200_set_device_rng_", 1)
+        _flag(L, "chase_b200_set_matrix_resident_", 0)
         solver.solve(deg=20, tol=tol, copy=False)
         rs2, secs2, _ = timed(a.steps)
         rel = max(rel, max(check(x) for x in rs2))
         es = H.itemsize
         e2e = {"value": sum(x.stats["gflop_filter"] for x in rs2) * 1e9 / secs2 / 1e12, "unit": "TFLOP/s",
-               "h2d_bytes_per_step": (N * N * es) + G * len(gr) * m * es,
-               "d2h_bytes_per_step": G * (len(gr) * m * es + 2 * m * 8), "time_to_solution_s": secs2 / a.steps,
-               "iterations": rs2[-1].iterations, "filtered_vecs": rs2[-1].filtered_vecs,
-               "start_vectors": "reference CPU stream (mt19937(1337)+normal; rows of this grid row generated on the host at "
-                                "the first solve, kept on the device afterwards)"}
+               "h2d_bytes_per_step": N * N * es, "d2h_bytes_per_step": G * (len(gr) * m * es + 2 * m * 8),
+               "time_to_solution_s": secs2 / a.steps, "iterations": rs2[-1].iterations,
+               "filtered_vecs": rs2[-1].filtered_vecs,
+               "start_vectors": "device Philox RNG, regenerated inside every timed step (the reference GPU backend "
+                                "regenerates with cuRAND every solve); nothing is cached between steps"}
     solver.finalize()
+    del Hh, Vh
+    _flag(L, "chase_b200_set_matrix_resident_", 0)
+
+    # ---- extra arms (not the headline): the round-1 weak-scaled C2 and a fixed complex problem ------------------------
+    extras = {}
+    if not getattr(a, "no_extras", False):
+        if G > 1:
+            extras["weak"] = extra_arm(world, "d", weak_n(G), nev, nex, nb, 2, "c2 weak-scaled (N = 20000 sqrt(G))")
+        extras["complex_fixed"] = extra_arm(world, "z", 24000, 1000, 400, nb, 2, "fixed complex problem")
 
     if rank == 0:
         roofline = {"bound": "tensor", "kernel": "hemm_tma_kernel (FP64 DMMA, TMA-fed; local A and A^H blocks)",
-                    "achieved": kern_tf, "peak": peak, "unit": "TFLOP/s", "frac": kern_tf / peak, "traffic": None,
+                    "achieved": kern_tf, "peak": peak, "unit": "TFLOP/s", "frac": kern_tf / peak,
+                    "traffic": hemm_traffic(f"c2_g{G}"),
                     "peak_source": "measured live per GPU: register-resident DMMA.8x8x4 loop (chase_b200_dmma_peak)",
                     "launches": int(hp[0]), "kernel_ms_total": hp[1], "kernel_share_of_step": hp[1] * 1e-3 / secs,
                     "achieved_min_over_ranks": kern_tf_min, "per": "GPU (rank 0)"}
         line = {
             "metric": "filter_hemm_tflops_per_time_to_solution", "value": value, "unit": "TFLOP/s", "n_gpus": G,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"c2 weak-scaled: d N={N} nev={nev} nex={nex} uniform spectrum, dense Q diag Q^H, "
-                                   f"tol 1e-10 deg 20 opt; {r}x{c} grid, block-cyclic {nb}x{nb}, NCCL",
-                       "l2": "inputs larger than L2 (local A block is %.1f GB)" % (len(gr) * len(gc) * H.itemsize / 1e9),
-                       "start_vectors": "device Philox RNG (value) / reference CPU stream (e2e)"},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"c2: d N={N} nev={nev} nex={nex} uniform spectrum, dense Q diag Q^H, "
+                                   f"tol 1e-10 deg 20 opt (the same problem at every GPU count); {r}x{c} grid, "
+                                   f"block-cyclic {nb}x{nb}, NCCL",
+                       "l2": "inputs larger than L2 (local A block is %.2f GB)" % (len(gr) * len(gc) * H.itemsize / 1e9),
+                       "start_vectors": "device Philox RNG, regenerated every solve (value and e2e)"},
             "time_to_solution_s": secs / a.steps, "iterations": rs[-1].iterations, "filtered_vecs": rs[-1].filtered_vecs,
             "filter_phase_tflops": st["gflop_filter"] / st["t_filter"] / 1e3 if st["t_filter"] > 0 else None,
-            "phases_s": {k[2:]: st[k] for k in ("t_all", "t_initvecs", "t_lanczos", "t_filter", "t_qr", "t_rr", "t_resid")},
+            "phases_s": phases, "phases_s_note": "last timed solve, max over ranks",
             "max_rel_eig_err": rel, "gpu_launches": int(launches), "gpu_launches_per": "rank 0", "clocks": clocks,
             "roofline": roofline, "e2e": e2e,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     world.close()
     if tdist.is_initialized():

@@ -795,7 +795,10 @@ public:
             std::iota(order.begin(), order.begin() + unconverged, 0);
             std::sort(order.begin(), order.begin() + std::size_t(1.0 * unconverged),
                       [&](int a, int b) { return (ritzv[a] < ritzv[b]); });
-            next_lower = ritzv[order[std::size_t(unconverged * 0.95) - 1]] * config.GetDecayingRate();
+            // reference: order[size_t(unconverged * 0.95) - 1] (algorithm.inc:2130) reads order[SIZE_MAX] when a single
+            // pair is left; clamped here (identical for unconverged >= 2)
+            next_lower = ritzv[order[std::max<std::size_t>(std::size_t(unconverged * 0.95), 1) - 1]] *
+                         config.GetDecayingRate();
 
             new_converged = locking_pseudo(single, unconverged, nex, tol, index.data(), ritzv, resid, residLast,
                                            &early_locked, locked, iteration);

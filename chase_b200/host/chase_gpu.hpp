@@ -409,9 +409,11 @@ public:
         int sweeps = 0;
         int rc = KK::heev((int64_t)block, dG_, (int64_t)ldg_, dZ_, (int64_t)ldg_, w.data(), heev_ws_, heev_ws_bytes_,
                           &sweeps, stream_);
-        if (rc != 0)
+        if (rc < 0)
             throw std::runtime_error("chase_b200: Hermitian eigensolver failed in RR (rc=" + std::to_string(rc) + ")");
         heev_sweeps_ += sweeps;
+        if (rc > 0) // sweep limit reached: the decomposition is still usable, the residual check guards accuracy
+            std::fprintf(stderr, "chase_b200: warning: Jacobi eigensolver stopped at its sweep limit (%d sweeps)\n", sweeps);
         for (std::size_t i = 0; i < block; ++i)
             ritzv[i] = (R)w[i];
         // residual block while A Q is at hand: R = (A Q) Z - (Q Z) Theta  (the reference runs a second A V,
@@ -776,10 +778,12 @@ private:
         std::vector<double> w((std::size_t)n);
         int sweeps = 0;
         const int rc = KK::heev(n, dM_, ldg, dZ_, ldg, w.data(), heev_ws_, heev_ws_bytes_, &sweeps, stream_);
-        if (rc != 0)
+        if (rc < 0)
             throw std::runtime_error("chase_b200: Hermitian eigensolver failed in the pseudo-Hermitian RR (rc=" +
                                      std::to_string(rc) + ")");
         heev_sweeps_ += sweeps;
+        if (rc > 0) // sweep limit reached: the decomposition is still usable, the residual check guards accuracy
+            std::fprintf(stderr, "chase_b200: warning: Jacobi eigensolver stopped at its sweep limit (%d sweeps)\n", sweeps);
         for (int64_t i = 0; i < n; ++i)
             ritzv[i] = R(1.0) / (R)(-w[(std::size_t)i]);
         CB2_KCHECK(KK::gemm(0, 0, n, (int64_t)block, n, 1.0, 0.0, dRinv_, ldg, dZ_, ldg, 0.0, 0.0, dT_, ldg, 0, nullptr,
@@ -871,11 +875,14 @@ private:
                 throw std::runtime_error("chase_b200: the Lanczos tridiagonal eigensolver did not converge");
     }
 
+    // every buffer tracks its own capacity: (M, numvec) may change between solves on the same object in ways that
+    // shrink M * numvec but grow M * M * numvec or numvec + 1
     void ensure_lanczos_buffers(std::size_t M, std::size_t numvec)
     {
         if (lan_nv_ < numvec)
         {
             lan_v_ = alloc<T>(3 * ld_ * numvec);
+            lan_rb_ = alloc<double>(numvec + 1);
             lan_nv_ = numvec;
         }
         if (lan_m_ < M * numvec)
@@ -883,9 +890,12 @@ private:
             lan_d_ = alloc<double>(M * numvec);
             lan_e_ = alloc<double>(M * numvec);
             lan_w_ = alloc<double>(M * numvec);
-            lan_Z_ = alloc<double>(M * M * numvec);
-            lan_rb_ = alloc<double>(numvec + 1);
             lan_m_ = M * numvec;
+        }
+        if (lan_z_ < M * M * numvec)
+        {
+            lan_Z_ = alloc<double>(M * M * numvec);
+            lan_z_ = M * M * numvec;
         }
     }
 
@@ -964,7 +974,7 @@ private:
     int *dInfo_ = nullptr, *dIdx_ = nullptr;
     T* lan_v_ = nullptr;
     double *lan_d_ = nullptr, *lan_e_ = nullptr, *lan_w_ = nullptr, *lan_Z_ = nullptr, *lan_rb_ = nullptr;
-    std::size_t lan_nv_ = 0, lan_m_ = 0;
+    std::size_t lan_nv_ = 0, lan_m_ = 0, lan_z_ = 0;
     std::vector<void*> allocs_;
     std::vector<R> resid_;
     std::vector<int> perm_;

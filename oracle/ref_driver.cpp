@@ -18,7 +18,7 @@
 //
 // Usage:
 //   chase_ref_cpu_<d|z|s|c> --N n --nev k --nex x --matrix clement|uniform|uniform_dense|file:<path>
-//        [--tol t] [--deg d] [--opt 0|1] [--maxiter i] [--seq k] [--perturb p]
+//        [--tol t] [--deg d] [--opt 0|1] [--maxiter i] [--seq k] [--perturb p] [--repeat k]
 //        [--vecs file] [--out result.json] [--dump-eigvecs file] [--initvecs-only file]
 //        [--numlanczos n] [--lanczositer m]
 //
@@ -132,6 +132,7 @@ int main(int argc, char** argv)
     double tol = -1, perturb = 1e-4;
     long deg = -1, numlanczos = -1, lanczositer = -1;
     int opt = 1;
+    bool fresh = false; // --repeat k: the SAME problem k times from fresh random vectors (warm-up + timed repeats)
     for (int i = 1; i + 1 < argc; i += 2)
     {
         std::string a = argv[i], v = argv[i + 1];
@@ -144,6 +145,7 @@ int main(int argc, char** argv)
         else if (a == "--opt") opt = std::stoi(v);
         else if (a == "--maxiter") maxiter = std::stoul(v);
         else if (a == "--seq") seq = std::stoul(v);
+        else if (a == "--repeat") { seq = std::stoul(v); fresh = true; }
         else if (a == "--perturb") perturb = std::stod(v);
         else if (a == "--out") out = v;
         else if (a == "--dump-eigvecs") dump_vecs = v;
@@ -289,8 +291,8 @@ int main(int argc, char** argv)
                   << " filtered_vecs " << pd.get_filtered_vecs() << " All "
                   << tm[0].count() << " s Filter " << tm[3].count() << " s\n";
 
-        config.SetApprox(true);
-        if (idx + 1 < seq)
+        config.SetApprox(!fresh);
+        if (idx + 1 < seq && !fresh)
         {
             // element-wise Hermitian perturbation, tests/noinput.cpp:120-134
             for (std::size_t i = 1; i < N; ++i)
