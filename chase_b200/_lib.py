@@ -36,6 +36,8 @@ def lib():
         _lib.chase_b200_trsm_ws_bytes.argtypes = [ctypes.c_int64, ctypes.c_int]
         _lib.chase_b200_heev_ws_bytes.restype = ctypes.c_size_t
         _lib.chase_b200_heev_ws_bytes.argtypes = [ctypes.c_int64, ctypes.c_int]
+        _lib.chase_b200_hemm_tf32_scratch_bytes.restype = ctypes.c_size_t
+        _lib.chase_b200_hemm_tf32_scratch_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
         _lib.chase_b200_launch_count.restype = ctypes.c_ulonglong
         _lib.chase_b200_trace_copy_.restype = ctypes.c_size_t
         _lib.chase_b200_trace_copy_.argtypes = [ctypes.c_char_p, ctypes.c_size_t]

@@ -128,7 +128,6 @@ struct HemmParams
     double* scratch;     // gridDim.x slots of BM*BN accumulators for incomplete tiles
     unsigned* flags;     // one per CTA: epoch of the launch whose head part is parked in the slot
     unsigned epoch;
-    int pipe;            // != 0: consumers prefetch across k-block boundaries (see the consumer loop)
 };
 
 // Stream-K work distribution.  The iteration space (tiles x k-blocks) is cut into gridDim.x equal contiguous spans,
@@ -223,9 +222,6 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
     using CF = HemmCfg<CPLX>;
     constexpr int BM = CF::BM, BN = CF::BN, BK = CF::BK, WM = CF::WM, WN = CF::WN, EPB = CF::EPB, ELEM = CF::ELEM;
     constexpr int MI = WM / 8, NJ = WN / 8, STAGES = CF::STAGES, KSTEPS = CF::KSTEPS;
-    constexpr int NWN = BN / WN;           // warps along n
-    constexpr int B_JSTRIDE = NWN * 8 * 128; // bytes between a warp's consecutive 8-column groups in a B stage
-    static_assert(KSTEPS % 2 == 0, "the cross-k-block prefetch alternates two fragment buffers");
     constexpr int IMUL = CPLX ? 2 : 1; // the tensor maps see complex<double> as two FLOAT64
 
     extern __shared__ unsigned char smem_raw[];
@@ -324,9 +320,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
             }
         }
         {
-            // 8-column groups are dealt round-robin to the NWN warps of a tile row (group = j * NWN + wn), so a ragged
-            // last tile spreads its valid groups over all warps instead of filling the first ones
-            const int n = wn * 8 + ncol;
+            const int n = wn * WN + ncol;
             const int byte_in = kin * ELEM;
             b_off[ks] = CF::A_BYTES + n * 128 + ((((byte_in >> 4) ^ (n & 7)) << 4) | (byte_in & 15));
         }
@@ -354,7 +348,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
         // Ragged last N tile: 8-column groups beyond k are skipped (warp-uniform), so a tile with <= BN/2 valid columns
         // keeps only one warp per SM sub-partition busy and costs about half a tile.
         const int nvalid = (int)((p.k - n0) < (long long)BN ? (p.k - n0) : (long long)BN);
-        int jmax = ((nvalid + 7) / 8 - wn + NWN - 1) / NWN; // groups j * NWN + wn < ceil(nvalid / 8)
+        int jmax = (nvalid - wn * WN + 7) / 8;
         jmax = jmax < 0 ? 0 : (jmax > NJ ? NJ : jmax);
 
         auto k_block = [&](const unsigned char* st, auto full_tag)
@@ -375,7 +369,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j)
                     if (FULL || j < jmax)
-                        fb[j] = *reinterpret_cast<const C_*>(st + b_off[ks] + j * B_JSTRIDE);
+                        fb[j] = *reinterpret_cast<const C_*>(st + b_off[ks] + j * (8 * 128));
                 if constexpr (!CPLX)
                 {
 #pragma unroll
@@ -410,96 +404,6 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
             }
         };
 
-        // fragments of one mma k-step (all NJ column groups)
-        auto load_frags = [&](const unsigned char* st, const int ks, C_* fa, C_* fb)
-        {
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-            {
-                const int h = (AH == 2) ? (i & 1) : 0;
-                const int g = (AH == 2) ? (i >> 1) : i;
-                fa[i] = *reinterpret_cast<const C_*>(st + a_off[h][ks] + g * A_ISTRIDE);
-            }
-#pragma unroll
-            for (int j = 0; j < NJ; ++j)
-                fb[j] = *reinterpret_cast<const C_*>(st + b_off[ks] + j * B_JSTRIDE);
-        };
-        auto mma_step = [&](const C_* fa, const C_* fb)
-        {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j)
-            {
-                if constexpr (!CPLX)
-                {
-#pragma unroll
-                    for (int i = 0; i < MI; ++i)
-                        dmma884(accr[j][i][0], accr[j][i][1], fb[j], fa[i]);
-                }
-                else
-                {
-                    const double bre = fb[j].re, bim = fb[j].im;
-                    const double s_ri = TA ? fb[j].im : -fb[j].im;
-                    const double s_ir = TA ? -fb[j].re : fb[j].re;
-#pragma unroll
-                    for (int i = 0; i < MI; ++i)
-                    {
-                        dmma884(accr[j][i][0], accr[j][i][1], bre, fa[i].re);
-                        dmma884(accr[j][i][0], accr[j][i][1], s_ri, fa[i].im);
-                        dmma884(acci[j][i][0], acci[j][i][1], s_ir, fa[i].im);
-                        dmma884(acci[j][i][0], acci[j][i][1], bim, fa[i].re);
-                    }
-                }
-            }
-        };
-
-        if (p.pipe && jmax == NJ && sp.kt_begin < sp.kt_end)
-        {
-            // Software pipeline across k-blocks.  All eight consumer warps reach a k-block boundary at the same
-            // time, so a blocking barrier wait + the first fragment loads (~150 cycles) used to idle the DMMA pipe
-            // once per k-block (3 % at 4096 pipe cycles per block).  Here the next stage's barrier is awaited one
-            // k-block ahead, and the first fragments of the next k-block are in flight before the last k-step of this
-            // one is issued.
-            C_ fa0[MI], fb0[NJ], fa1[MI], fb1[NJ];
-            const bool early = (warp & 4) == 0;
-            {
-                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(bars + 8 * s, ph);
-                load_frags(gen_base + s * CF::STAGE_BYTES, 0, fa0, fb0);
-            }
-            for (int kt = sp.kt_begin; kt < sp.kt_end; ++kt, ++it)
-            {
-                const uint32_t s = it % STAGES;
-                const unsigned char* st = gen_base + s * CF::STAGE_BYTES;
-                const uint32_t itn = it + 1, sn = itn % STAGES, phn = (itn / STAGES) & 1;
-                const bool more = kt + 1 < sp.kt_end;
-                // the look-ahead wait (a 60-90 cycle stall even when the phase is already complete) sits at a
-                // different point of the k-block for the two warps that share an SM sub-partition (w, w + 4), so one
-                // of them always feeds the DMMA pipe
-                if (more && early)
-                    mbar_wait(bars + 8 * sn, phn);
-                load_frags(st, 1, fa1, fb1);
-                mma_step(fa0, fb0);
-                if constexpr (KSTEPS == 4)
-                {
-                    load_frags(st, 2, fa0, fb0);
-                    mma_step(fa1, fb1);
-                    if (more && !early)
-                        mbar_wait(bars + 8 * sn, phn);
-                    load_frags(st, 3, fa1, fb1);
-                    mma_step(fa0, fb0);
-                }
-                else if (more && !early)
-                    mbar_wait(bars + 8 * sn, phn);
-                if (more)
-                    load_frags(gen_base + sn * CF::STAGE_BYTES, 0, fa0, fb0);
-                mma_step(fa1, fb1);
-                static_assert(KSTEPS == 2 || KSTEPS == 4, "unrolled by hand for 2 or 4 k-steps");
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(bars + 8 * (STAGES + s));
-            }
-        }
-        else
         for (int kt = sp.kt_begin; kt < sp.kt_end; ++kt, ++it)
         {
             const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
@@ -572,7 +476,7 @@ __global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
         {
-            const long long n = n0 + 8 * (j * NWN + wn) + ncol;
+            const long long n = n0 + wn * WN + 8 * j + ncol;
             if (n >= p.k)
                 continue;
             // g = -alpha * shift_j
@@ -740,12 +644,6 @@ inline bool hemm_hybrid_enabled(bool ta)
     const char* e = getenv("CHASE_B200_HEMM_HYBRID");
     return e ? atoi(e) != 0 : !ta;
 }
-// CHASE_B200_HEMM_PIPE=0 selects the plain consumer loop (blocking wait at every k-block); read at every launch
-inline bool hemm_pipe_enabled()
-{
-    const char* e = getenv("CHASE_B200_HEMM_PIPE");
-    return e ? atoi(e) != 0 : true;
-}
 inline bool hemm_streamk_disabled()
 {
     static int v = -1;
@@ -856,7 +754,6 @@ inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Tr
     p.scratch = sc->slots;
     p.flags = sc->flags;
     p.epoch = ++sc->epoch;
-    p.pipe = hemm_pipe_enabled() ? 1 : 0;
     if (ta)
     {
         CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

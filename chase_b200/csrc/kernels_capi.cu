@@ -8,6 +8,7 @@
 #include "householder.cuh"
 #include "jacobi.cuh"
 #include "osj.cuh"
+#include "tf32_api.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -159,6 +160,28 @@ int hemm_rect_impl(int ta, int64_t M, int64_t K, int64_t k, double are, double a
     }
     else
     {
+        // registered TF32 split of A: tcgen05 kind::tf32 kernel (hemm_tf32.cuh)
+        Tf32Reg tr;
+        if (K > 0 && tf32_lookup(A, &tr) && tr.ld == lda)
+        {
+            int64_t sflip = 0;
+            bool ok = ta != 0; // C = A^H B is the kernel's native orientation
+            if (!ta && M == K && tr.kind == 0)
+                ok = true; // Hermitian: A B = A^H B on the same storage
+            if (!ta && M == K && tr.kind == 1)
+            {
+                ok = true; // pseudo-Hermitian: H B = S H^H (S B)
+                sflip = M / 2;
+            }
+            if (ok)
+            {
+                auto fn = Traits<T>::cplx ? chase_b200_hemm_tf32_c : chase_b200_hemm_tf32_s;
+                const int rc = fn(M, K, k, are, aim, A, tr.lo, lda, B, ldb, bre, bim, C, ldc, shift, theta, sflip,
+                                  tf32_terms(), tr.scratch, tr.scratch_bytes, stream);
+                if (rc != -5 && rc != -3)
+                    return rc;
+            }
+        }
         using TW = typename WideOf<T>::type;
         auto it = wide_registry().find(A);
         if (it != wide_registry().end() && K > 0)

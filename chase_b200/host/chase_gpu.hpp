@@ -137,16 +137,34 @@ public:
             perm_[i] = (int)i;
         const char* e = std::getenv("CHASE_B200_DEVICE_RNG");
         device_rng_ = e && std::atoi(e) != 0;
-        // FP32 storage: keep an FP64 copy of A so that the filter products run on the TMA + DMMA kernel (the generic
-        // kernel reaches 19 of 37 TFLOP/s); costs 2x the matrix memory, CHASE_B200_FP32_WIDEN=0 turns it off
-        const char* w = std::getenv("CHASE_B200_FP32_WIDEN");
-        if (sizeof(R) == 4 && !(w && std::atoi(w) == 0))
+        // FP32 storage.  Default: the tcgen05 kind::tf32 kernel with 3x/4x TF32 splitting (csrc/hemm_tf32.cuh): the
+        // matrix as stored is the hi operand, one extra FP32 array holds the lo part (2x the matrix memory).
+        // CHASE_B200_FP32_PATH=fp64copy: the round-1 route through an FP64 copy on the DMMA kernel (3x memory);
+        // =generic (or CHASE_B200_FP32_WIDEN=0): the generic kernel that widens tiles on the fly.
+        if (sizeof(R) == 4)
         {
-            wide_scratch_bytes_ = 2 * ld_ * nc_ * 2 * sizeof(T);
-            dHw_ = alloc<unsigned char>(ld_ * N_ * 2 * sizeof(T));
-            wide_scratch_ = alloc<unsigned char>(wide_scratch_bytes_);
-            chase_b200_widen_register(dH_, dHw_, (int64_t)ld_, (int64_t)N_, (int64_t)N_, wide_scratch_,
-                                      wide_scratch_bytes_);
+            std::string path = "tf32";
+            if (const char* e = std::getenv("CHASE_B200_FP32_PATH"))
+                path = e;
+            const char* w = std::getenv("CHASE_B200_FP32_WIDEN");
+            if (w && std::atoi(w) == 0)
+                path = "generic";
+            if (path == "tf32")
+            {
+                dHl_ = alloc<T>(ld_ * N_);
+                tf32_scratch_bytes_ = chase_b200_hemm_tf32_scratch_bytes((int64_t)N_, (int64_t)nc_, (int)sizeof(T));
+                tf32_scratch_ = alloc<unsigned char>(tf32_scratch_bytes_);
+                chase_b200_tf32_register(dH_, dHl_, (int64_t)ld_, (int64_t)N_, (int64_t)N_, kPseudo ? 1 : 0,
+                                         tf32_scratch_, tf32_scratch_bytes_);
+            }
+            else if (path == "fp64copy")
+            {
+                wide_scratch_bytes_ = 2 * ld_ * nc_ * 2 * sizeof(T);
+                dHw_ = alloc<unsigned char>(ld_ * N_ * 2 * sizeof(T));
+                wide_scratch_ = alloc<unsigned char>(wide_scratch_bytes_);
+                chase_b200_widen_register(dH_, dHw_, (int64_t)ld_, (int64_t)N_, (int64_t)N_, wide_scratch_,
+                                          wide_scratch_bytes_);
+            }
         }
     }
     // the reference's second constructor: H as a (host-backed) matrix object (chase_gpu.hpp:195-267)
@@ -159,6 +177,8 @@ public:
     {
         if (dHw_)
             chase_b200_widen_unregister(dH_);
+        if (dHl_)
+            chase_b200_tf32_unregister(dH_);
         for (void* p : allocs_)
             cudaFree(p);
         if (stream_)
@@ -212,6 +232,8 @@ public:
             matrix_on_device_ = true;
             if (dHw_)
                 CB2_KCHECK(chase_b200_widen_sync(kCplx ? 'c' : 's', dH_, stream_));
+            if (dHl_)
+                CB2_KCHECK(chase_b200_tf32_sync(kCplx ? 'c' : 's', dH_, stream_));
         }
         reset_perm();
         shift_ = 0.0;
@@ -399,9 +421,12 @@ public:
         }
         T* Q = dV1_ + locked_ * ld_;
         T* W = dV2_ + locked_ * ld_;
-        // W = A Q   (the reference forms A^H Q; A is Hermitian)
+        // W = A Q   (the reference forms A^H Q; A is Hermitian).  FP32 types: 4 TF32 partial products (full FP32
+        // operand precision) for the projected matrix and the residual block, 3 in the filter
+        chase_b200_tf32_set_terms(4);
         CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)block, 1.0, 0.0, dH_, (int64_t)ld_, Q, (int64_t)ld_, 0.0, 0.0, W,
                             (int64_t)ld_, 0.0, nullptr, stream_));
+        chase_b200_tf32_set_terms(3);
         // G = W^H Q
         CB2_KCHECK(KK::gemm(1, 0, (int64_t)block, (int64_t)block, (int64_t)N_, 1.0, 0.0, W, (int64_t)ld_, Q,
                             (int64_t)ld_, 0.0, 0.0, dG_, (int64_t)ldg_, 0, splitk_ws_, splitk_ws_bytes_, stream_));
@@ -456,8 +481,10 @@ public:
             CB2_CHECK(cudaMemcpyAsync(dTheta_, th.data(), k * sizeof(double), cudaMemcpyHostToDevice, stream_));
             T* V = dV1_ + locked_ * ld_;
             // W = A V - V diag(theta), shift folded into the HEMM epilogue
+            chase_b200_tf32_set_terms(4);
             CB2_KCHECK(KK::hemm((int64_t)N_, (int64_t)k, 1.0, 0.0, dH_, (int64_t)ld_, V, (int64_t)ld_, 0.0, 0.0, W,
                                 (int64_t)ld_, 0.0, dTheta_, stream_));
+            chase_b200_tf32_set_terms(3);
         }
         resid_ready_ = false;
         CB2_KCHECK(KK::colnorms((int64_t)N_, (int64_t)k, W, (int64_t)ld_, dNorms_, 1, stream_));
@@ -750,7 +777,9 @@ private:
         const int64_t ld = (int64_t)ld_, ldg = (int64_t)ldg_;
         T* Q = dV1_ + locked_ * ld_;
         T* W = dV2_ + locked_ * ld_;
+        chase_b200_tf32_set_terms(4);
         CB2_KCHECK(KK::hemm(N, n, 1.0, 0.0, dH_, ld, Q, ld, 0.0, 0.0, W, ld, 0.0, nullptr, stream_));
+        chase_b200_tf32_set_terms(3);
         CB2_KCHECK(KK::scale_rows(N - half, n, W + half, ld, -1.0, stream_));
         CB2_KCHECK(KK::gemm(1, 0, n, n, N, 1.0, 0.0, Q, ld, W, ld, 0.0, 0.0, dG_, ldg, 0, splitk_ws_, splitk_ws_bytes_,
                             stream_));
@@ -966,6 +995,9 @@ private:
     T *dM_ = nullptr, *dRinv_ = nullptr, *dT_ = nullptr; // pseudo-Hermitian RR only
     unsigned char *dHw_ = nullptr, *wide_scratch_ = nullptr; // FP64 copy of an FP32 matrix + panel scratch
     std::size_t wide_scratch_bytes_ = 0;
+    T* dHl_ = nullptr; // lo part of the TF32 split of an FP32 matrix (tcgen05 path)
+    unsigned char* tf32_scratch_ = nullptr;
+    std::size_t tf32_scratch_bytes_ = 0;
     double* ones_ = nullptr;
     T* dV0_ = nullptr; // device copy of the reference start block (parity mode), filled at the first random solve
     unsigned char *heev_ws_ = nullptr, *trsm_ws_ = nullptr, *splitk_ws_ = nullptr, *hh_ws_ = nullptr;

@@ -84,6 +84,40 @@ def hemm_rect(ta, M, K, k, alpha, A, lda, B, ldb, beta, C, ldc):
                   _stream()), "hemm_rect")
 
 
+def tf32_lo(A, cplx: bool):
+    """lo part of the TF32 split of the FP32 (or interleaved complex FP32) device array A (same shape)."""
+    import torch
+
+    L = lib()
+    lo = torch.empty_like(A)
+    ld = A.shape[-1]
+    cols = A.numel() // ld
+    _chk(L.chase_b200_tf32_register(_ptr(A), _ptr(lo), ctypes.c_int64(ld), ctypes.c_int64(ld), ctypes.c_int64(cols), 2,
+                                    ctypes.c_void_p(0), ctypes.c_size_t(0)), "tf32_register")
+    _chk(L.chase_b200_tf32_sync(ctypes.c_char(b"c" if cplx else b"s"), _ptr(A), _stream()), "tf32_sync")
+    L.chase_b200_tf32_unregister(_ptr(A))
+    return lo
+
+
+def hemm_tf32(M, K, k, alpha, A, Alo, lda, B, ldb, beta, C, ldc, shift=0.0, theta=None, sflip=0, terms=3):
+    """C(M x k) <- alpha S (A^s)^H S B + beta C - alpha shift_j B on the tcgen05 kind::tf32 kernel; A^s is K x M."""
+    import torch
+
+    L = lib()
+    sfx = _sfx(C)
+    es = C.element_size()
+    nbytes = L.chase_b200_hemm_tf32_scratch_bytes(K, k, es)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=C.device)
+    f = getattr(L, f"chase_b200_hemm_tf32_{sfx}")
+    ar, ai = _c(alpha)
+    br, bi = _c(beta)
+    rc = f(ctypes.c_int64(M), ctypes.c_int64(K), ctypes.c_int64(k), ar, ai, _ptr(A), _ptr(Alo), ctypes.c_int64(lda),
+           _ptr(B), ctypes.c_int64(ldb), br, bi, _ptr(C), ctypes.c_int64(ldc), ctypes.c_double(shift), _ptr(theta),
+           ctypes.c_int64(sflip), int(terms), _ptr(scratch), ctypes.c_size_t(nbytes), _stream())
+    torch.cuda.current_stream().synchronize()  # scratch is a temporary
+    return _chk(rc, "hemm_tf32")
+
+
 def potrf(n, G, ldg, info):
     f = getattr(lib(), f"chase_b200_potrf_{_sfx(G)}")
     return _chk(f(ctypes.c_int64(n), _ptr(G), ctypes.c_int64(ldg), _ptr(info), _stream()), "potrf")

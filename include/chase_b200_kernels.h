@@ -168,6 +168,31 @@ extern "C"
                                   size_t scratch_bytes);
     int chase_b200_widen_unregister(const void* A);
     int chase_b200_widen_sync(char type, const void* A, void* stream);
+    /* Single-precision value types on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM accumulators,
+       TMA-fed; csrc/hemm_tf32.cuh):  C(M x k) <- alpha S (A^s)^H S B + beta C - alpha shift_j B  with the stored matrix
+       A^s K x M column-major, 3 (or 4) TF32 partial products per operand pair.  Alo = the lo part of the TF32 split of
+       A^s (same shape and ld; chase_b200_tf32_sync writes it), sflip > 0 negates rows >= sflip of the panel and of the
+       product (pseudo-Hermitian H = S H^H S), scratch >= chase_b200_hemm_tf32_scratch_bytes(K, k, sizeof element).
+       Replaces cublasSgemm / cublasCgemm (reference external/cublaspp/cublaspp.hpp:563, 623).  Returns -5 when the
+       shape / alignment is not supported (callers fall back to the generic kernel). */
+    int chase_b200_hemm_tf32_s(int64_t M, int64_t K, int64_t k, double are, double aim, const void* A, const void* Alo,
+                               int64_t lda, const void* B, int64_t ldb, double bre, double bim, void* C, int64_t ldc,
+                               double shift, const double* theta, int64_t sflip, int terms, void* scratch,
+                               size_t scratch_bytes, void* stream);
+    int chase_b200_hemm_tf32_c(int64_t M, int64_t K, int64_t k, double are, double aim, const void* A, const void* Alo,
+                               int64_t lda, const void* B, int64_t ldb, double bre, double bim, void* C, int64_t ldc,
+                               double shift, const double* theta, int64_t sflip, int terms, void* scratch,
+                               size_t scratch_bytes, void* stream);
+    size_t chase_b200_hemm_tf32_scratch_bytes(int64_t K, int64_t k, int elem_bytes);
+    /* Registry: chase_b200_hemm[_rect]_{s,c} calls whose A is a registered pointer run on the kernel above.
+       kind 0: A Hermitian (A B = A^H B), 1: pseudo-Hermitian (S A Hermitian), 2: general block (only op(A) = A^H).
+       chase_b200_tf32_sync(type 's' | 'c') recomputes Alo after A changed; chase_b200_tf32_set_terms(3 | 4) selects
+       the number of partial products of the following calls (4: A_lo B_lo included, for the RR / residual products). */
+    int chase_b200_tf32_register(const void* A, void* Alo, int64_t ld, int64_t rows, int64_t cols, int kind,
+                                 void* scratch, size_t scratch_bytes);
+    int chase_b200_tf32_unregister(const void* A);
+    int chase_b200_tf32_sync(char type, const void* A, void* stream);
+    void chase_b200_tf32_set_terms(int terms);
     size_t chase_b200_trsm_ws_bytes(int64_t n, int elem_bytes);
     size_t chase_b200_hhqr_ws_bytes(int64_t rows, int64_t n, int elem_bytes);
     size_t chase_b200_heev_ws_bytes(int64_t n, int is_complex);

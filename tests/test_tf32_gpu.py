@@ -1,0 +1,103 @@
+"""The tcgen05 kind::tf32 filter product (chase_b200/csrc/hemm_tf32.cuh) against an FP64 statement of
+
+    C <- alpha S (A^s)^H S B + beta C - alpha shift_j B
+
+through the kernel C ABI (chase_b200_hemm_tf32_{s,c}), for float and complex<float>, ragged shapes, rectangular blocks,
+the pseudo-Hermitian sign flip and per-column shifts.  Tolerance: 3e-5 of the result's RMS, i.e. the error level of a
+plain FP32 GEMM (cuBLAS SGEMM measures 2e-6 .. 1.5e-5 on the same inputs); a TF32-only product would be at 1e-3."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+TOL = 3e-5
+
+
+def _run(cplx, M, K, kc, alpha, beta, shift=0.0, sflip=0, terms=3, theta=False, seed=0):
+    from chase_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dt = torch.complex64 if cplx else torch.float32
+    wide = torch.complex128 if cplx else torch.float64
+    ldk, ldm = (K + 15) // 16 * 16, (M + 15) // 16 * 16
+
+    def rnd(r, c):
+        x = torch.randn((r, c), generator=g, device="cuda", dtype=torch.float32)
+        if cplx:
+            x = torch.complex(x, torch.randn((r, c), generator=g, device="cuda", dtype=torch.float32))
+        return x
+
+    A = torch.zeros((M, ldk), dtype=dt, device="cuda")  # the stored matrix, K x M column-major
+    A[:, :K] = rnd(M, K)
+    B = torch.zeros((kc, ldk), dtype=dt, device="cuda")
+    B[:, :K] = rnd(kc, K)
+    C = torch.full((kc, ldm), 7.0, dtype=dt, device="cuda")
+    C[:, :M] = rnd(kc, M)
+    C0 = C.clone()
+    th = torch.linspace(-1.0, 2.0, kc, dtype=torch.float64, device="cuda") if theta else None
+    Alo = k.tf32_lo(A, cplx)
+    k.hemm_tf32(M, K, kc, alpha, A, Alo, ldk, B, ldk, beta, C, ldm, shift=shift, theta=th, sflip=sflip, terms=terms)
+    torch.cuda.synchronize()
+    Aw, Bw, Cw = A[:, :K].to(wide), B[:, :K].to(wide), C0[:, :M].to(wide)
+    Bs = Bw.clone()
+    if sflip:
+        Bs[:, sflip:] *= -1
+    P = Bs @ Aw.conj().T
+    if sflip:
+        P[:, sflip:] *= -1
+    ref = alpha * P + beta * Cw
+    if theta:
+        ref = ref - alpha * th[:, None] * Bw[:, :M]
+    elif shift != 0.0:
+        ref = ref - alpha * shift * Bw[:, :M]
+    got = C[:, :M].to(wide)
+    scale = float(torch.linalg.norm(ref)) / np.sqrt(ref.numel())
+    err = float((got - ref).abs().max()) / scale
+    assert torch.equal(C[:, M:], C0[:, M:]), "padding rows written"
+    return err
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("terms", [3, 4])
+def test_tf32_square_filter_step(cplx, terms):
+    assert _run(cplx, 1000, 1000, 300, 0.7, -0.3, shift=1.5, terms=terms) < TOL
+
+
+@pytest.mark.parametrize("cplx,M,K,kc", [(False, 256, 256, 8), (False, 640, 2000, 130), (False, 129, 515, 257),
+                                          (True, 384, 1500, 70), (True, 131, 700, 129), (False, 2048, 6000, 700)])
+def test_tf32_rectangular_and_ragged(cplx, M, K, kc):
+    assert _run(cplx, M, K, kc, 1.0, 0.0) < TOL
+
+
+def test_tf32_long_accumulation_chain_stays_fp32_accurate():
+    """K = 16384: 2048 k-steps.  A single TMEM accumulation chain drifts by ~7e-4 here (truncating adds); the chunked
+    drain keeps the error at the FP32 level."""
+    assert _run(False, 256, 16384, 64, 1.0, 0.0) < TOL
+    assert _run(True, 256, 8192, 40, 1.0, 0.0) < TOL
+
+
+def test_tf32_pseudo_hermitian_sign_flip_and_column_shifts():
+    assert _run(True, 512, 512, 100, 1.0, 0.5, shift=-2.0, sflip=256, terms=4) < TOL
+    assert _run(True, 600, 600, 90, 1.0, 0.0, theta=True, terms=4) < TOL
+    assert _run(False, 600, 600, 90, 0.5, 0.25, theta=True, terms=4) < TOL
+
+
+def test_fp32_solves_use_the_tcgen05_kernel_and_follow_the_reference_schedule():
+    """FP32 problems through ?chase_ now run their HEMMs on the kind::tf32 kernel (no FP64 copy of the matrix): same
+    iteration count and filtered-vector count as the reference CPU solver's FP32 runs, eigenvalues to 1e-4."""
+    import chase_b200
+    from oracle import chase_oracle as co
+    from tests.golden_util import DT, load
+
+    for name in ("serial_clement_s_N256", "serial_clement_c_N256"):
+        g = load(name)
+        H = co.clement(g["N"], DT[g["type"]])
+        p = g["problems"][0]
+        with chase_b200.ChASE(H, g["nev"], g["nex"]) as s:
+            res = s.solve(deg=g["deg"], tol=g["tol"])
+        nev = g["nev"]
+        refv = np.array(p["ritzv"][:nev])
+        assert np.max(np.abs(res.ritzv[:nev] - refv) / np.abs(refv)) < 1e-4
+        assert np.all(res.resid[:nev] < 100 * g["tol"])
+        assert res.iterations == p["iterations"], (name, res.iterations, p["iterations"])
