@@ -33,7 +33,17 @@ bool tf32_lookup(const void* A, Tf32Reg* out)
     *out = it->second;
     return true;
 }
-int tf32_terms() { return g_terms; }
+int tf32_terms()
+{
+    // CHASE_B200_TF32_TERMS=3|4 forces the number of partial products of every call (diagnostics)
+    static int forced = -1;
+    if (forced < 0)
+    {
+        const char* e = std::getenv("CHASE_B200_TF32_TERMS");
+        forced = e ? std::atoi(e) : 0;
+    }
+    return forced >= 3 ? (forced >= 4 ? 4 : 3) : g_terms;
+}
 } // namespace cb2
 
 extern "C" int chase_b200_tf32_register(const void* A, void* Alo, int64_t ld, int64_t rows, int64_t cols, int kind,

@@ -67,6 +67,9 @@ __device__ __forceinline__ cxd load_u<cxd>(const JRot& R)
     return cxd{R.ure, R.uim};
 }
 
+__device__ __forceinline__ double jabs(double a) { return fabs(a); }
+__device__ __forceinline__ double jabs(cxd a) { return sqrt(a.re * a.re + a.im * a.im); }
+
 template <class C>
 __device__ __forceinline__ JRot make_rot(double app, double aqq, C apq, double thresh)
 {
@@ -78,12 +81,16 @@ __device__ __forceinline__ JRot make_rot(double app, double aqq, C apq, double t
     R.tapq = 0.0;
     R.active = 0;
     R.pad = 0;
-    const double ab = sqrt(cabs2(apq));
+    const double ab = jabs(apq);
     if (!(ab > thresh))
         return R;
-    const double th = (aqq - app) / (2.0 * ab);
-    const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
-    R.c = 1.0 / sqrt(t * t + 1.0);
+    // t = sign(zeta) 2|a_pq| / (|zeta| + sqrt(zeta^2 + 4|a_pq|^2)), zeta = a_qq - a_pp: the smaller root of
+    // t^2 + 2 theta t - 1 = 0 with theta = zeta / (2|a_pq|), written with one square root, one division and one
+    // reciprocal square root (the rotation sits on the critical path of every Jacobi step: 8 threads compute while
+    // the CTA waits)
+    const double zeta = aqq - app;
+    const double t = (zeta >= 0 ? 2.0 : -2.0) * ab / (fabs(zeta) + sqrt(zeta * zeta + 4.0 * ab * ab));
+    R.c = rsqrt(t * t + 1.0);
     R.s = t * R.c;
     R.tapq = t * ab;
     store_u(R, phase_of(apq, ab));

@@ -516,7 +516,9 @@ int heev_osj_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ld
         return -3;
     if (((uintptr_t)ws) & 15)
         return -3;
-    const int ldb = (n + 1) & ~1; // 16-byte aligned columns for the TMA bulk copies
+    // column stride: a multiple of 4 (16-byte aligned TMA bulk copies; whole 4-row k-steps for the DMMA round kernel),
+    // rows n .. ldb-1 are zero
+    const int ldb = (n + 3) & ~3;
     unsigned char* base = (unsigned char*)ws;
     const size_t nb = (size_t)ldb * n;
     C_* Bm = (C_*)base;
@@ -544,20 +546,48 @@ int heev_osj_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ld
         ++nblk;
     if (nblk < 2)
         nblk = 2;
-    // rows per chunk: all of them if 16 columns fit into 208 KB of shared memory
-    const int rmax = (int)(208 * 1024 / (OSJ_K * sizeof(C_))) / 32 * 32;
-    const int rpc = std::min((n + 31) / 32 * 32, rmax);
-    const size_t smem = (size_t)OSJ_K * rpc * sizeof(C_);
-    CB2_CUDA_OK(cudaFuncSetAttribute(osj_round_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const double tol = std::sqrt((double)n) * 2.220446049250313e-16;
     const int max_sweeps = 60;
+    // DMMA round kernel (default) or the register-tiled FMA kernel (CHASE_B200_OSJ_DMMA=0)
+    static const bool use_dmma = []
+    {
+        const char* e = getenv("CHASE_B200_OSJ_DMMA");
+        return !(e && atoi(e) == 0);
+    }();
+    int rpc, cs = 0;
+    size_t smem;
+    if (use_dmma)
+    {
+        // 16 columns of cs elements + the per-warp partial Gram blocks in <= 216 KB (+ 10 KB static); cs = rpc + 4 gives the
+        // conflict-free stride (32 / 64 bytes mod 128)
+        const int cs_max = (int)((216 * 1024 / sizeof(C_) - OsjDmma<C_>::NRED) / OSJ_K);
+        const int rmax = (cs_max - 4) / 32 * 32;
+        rpc = std::min((ldb + 31) / 32 * 32, rmax);
+        cs = rpc + 4;
+        smem = ((size_t)OSJ_K * cs + OsjDmma<C_>::NRED) * sizeof(C_);
+        CB2_CUDA_OK(cudaFuncSetAttribute(osj_round_dmma_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    else
+    {
+        // rows per chunk: all of them if 16 columns fit into 208 KB of shared memory
+        const int rmax = (int)(208 * 1024 / (OSJ_K * sizeof(C_))) / 32 * 32;
+        rpc = std::min((n + 31) / 32 * 32, rmax);
+        smem = (size_t)OSJ_K * rpc * sizeof(C_);
+        CB2_CUDA_OK(cudaFuncSetAttribute(osj_round_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     int sweep = 0, converged = 0;
     for (; sweep < max_sweeps; ++sweep)
     {
         CB2_CUDA_OK(cudaMemsetAsync(maxoff, 0, 32, st)); // maxoff and nrot
         for (int r = 0; r < nblk - 1; ++r)
-            osj_round_kernel<C_><<<nblk / 2, OSJ_THREADS, smem, kcount(st)>>>(n, ldb, rpc, nblk, r, Bm, tol, nrot,
-                                                                                maxoff);
+        {
+            if (use_dmma)
+                osj_round_dmma_kernel<C_><<<nblk / 2, OSJ_THREADS, smem, kcount(st)>>>(n, ldb, rpc, cs, nblk, r, Bm, tol,
+                                                                                         nrot, maxoff);
+            else
+                osj_round_kernel<C_><<<nblk / 2, OSJ_THREADS, smem, kcount(st)>>>(n, ldb, rpc, nblk, r, Bm, tol, nrot,
+                                                                                    maxoff);
+        }
         struct
         {
             unsigned long long bits;
@@ -568,6 +598,9 @@ int heev_osj_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ld
         CB2_CUDA_OK(cudaStreamSynchronize(st));
         double mo;
         std::memcpy(&mo, &h.bits, sizeof mo);
+        // mo = largest scaled off-diagonal seen BEFORE its rotation during this sweep.  (Stopping as soon as
+        // mo < 3e-8 "because the next sweep squares it" costs orthogonality inside clusters of eigenvalues: measured
+        // 1e-12 instead of 1e-14 on a 50-fold eigenvalue, so the verification sweep stays.)
         if (h.nr == 0 || mo < 64.0 * tol)
         {
             converged = 1;
@@ -996,7 +1029,7 @@ extern "C" size_t chase_b200_heev_ws_bytes(int64_t n, int is_complex)
 {
     const size_t ce = is_complex ? 16 : 8;
     const size_t np = (size_t)((n + 1) & ~(int64_t)1);
-    size_t b = 3 * (size_t)(n + 1) * n * ce; // one-sided path: B | T | Gs (the two-sided path uses the first two)
+    size_t b = 3 * (size_t)(n + 4) * n * ce; // one-sided path: B | T | Gs (the two-sided path uses the first two)
     b += (np / 2) * sizeof(JRot) + 16;
     b += 3 * (size_t)n * sizeof(double) + 64;
     b += (size_t)n * sizeof(int) + 64;

@@ -424,6 +424,364 @@ __global__ void __launch_bounds__(OSJ_THREADS) osj_round_kernel(int n, int ldb, 
     }
 }
 
+// ---- the same round on the FP64 tensor pipe --------------------------------------------------------------------
+// osj_round_kernel spends most of a round in shared-memory loads: its register-tiled FMAs read 0.4 (Gram) and 0.56
+// (update) LDS per FMA.  Here both phases are DMMA.8x8x4 products whose fragments come straight from the column
+// tiles (2 loads per 3 DMMAs in the Gram phase, 4 loads per 8 DMMAs in the update):
+//   Gram    M[I][J] (8x8) += conj(Bp[r..r+3, 8I..8I+7])^T Bp[r..r+3, 8J..8J+7]   -- the A fragment of block I and the B
+//           fragment of block J are the same register (lane l: row r + l%4, column 8I + l/4); warps split the rows,
+//           the per-warp partial sums are added in a fixed order (bit-reproducible: the distributed backend runs this
+//           solver redundantly on every GPU and relies on identical results).
+//   update  Y[r..r+7, 8J..8J+7] = sum_a Bp[r..r+7, 4a..4a+3] J[4a..4a+3, 8J..8J+7]  -- J fragments live in registers
+//           for the whole phase; a warp reads all 16 columns of its 8 rows before it overwrites them in place; the
+//           finished tile goes back with TMA bulk stores.
+// Column stride in shared memory: cs elements with cs * sizeof(C) = 32 (real) / 64 (complex) mod 128, which makes the
+// Gram fragment loads bank-conflict free.  ldb (global column stride) is a multiple of 4 with zero rows behind n, so
+// every 4-row k-step is fully defined.
+template <class C>
+struct OsjDmma
+{
+    static constexpr bool CPLX = sizeof(C) == 16;
+    static constexpr int NRED = 8 * 3 * 64; // per-warp partial Gram blocks (elements of C)
+};
+
+__device__ __forceinline__ void osj_bulk_store(void* dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                 : "memory");
+}
+
+template <class C>
+__global__ void __launch_bounds__(OSJ_THREADS) osj_round_dmma_kernel(int n, int ldb, int rpc, int cs, int nblk, int round,
+                                                                      C* B, double tol, int* nrot,
+                                                                      unsigned long long* maxoff_bits)
+{
+    constexpr int K = OSJ_K;
+    constexpr bool CPLX = OsjDmma<C>::CPLX;
+    extern __shared__ __align__(128) unsigned char osj_smem[];
+    C* sB = reinterpret_cast<C*>(osj_smem);          // [K][cs]
+    C* sRed = sB + (size_t)K * cs;                     // [8 warps][3 blocks][64]
+    __shared__ C sM[K][K + 1];
+    __shared__ C sJ[K][K];
+    __shared__ JRot sR[K / 2];
+    __shared__ int s_active;
+    __shared__ int s_col[K];
+    __shared__ __align__(8) unsigned long long s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lc = lane >> 2, lq = lane & 3;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    int bp, bq;
+    rr_pair(round, blockIdx.x, nblk, bp, bq);
+    if (bp > bq)
+    {
+        const int t = bp;
+        bp = bq;
+        bq = t;
+    }
+    if (tid < K)
+    {
+        const int c = (tid < OSJ_B) ? bp * OSJ_B + tid : bq * OSJ_B + (tid - OSJ_B);
+        s_col[tid] = (c < n) ? c : -1;
+    }
+    if (tid == 0)
+    {
+        s_active = 0;
+        osj_mbar_init(bar);
+    }
+    __syncthreads();
+    const int nchunks = (ldb + rpc - 1) / rpc;
+    uint32_t parity = 0;
+
+    // rows [r0, r0 + rows) of the 16 columns -> sB (missing columns are zero-filled); rows is a multiple of 4
+    auto load_chunk = [&](int r0, int rows)
+    {
+        for (int a = 0; a < K; ++a)
+            if (s_col[a] < 0)
+                for (int r = tid; r < rows; r += OSJ_THREADS)
+                    sB[(size_t)a * cs + r] = czero<C>();
+        if (tid == 0)
+        {
+            int ncols = 0;
+            for (int a = 0; a < K; ++a)
+                ncols += (s_col[a] >= 0);
+            osj_mbar_expect(bar, (uint32_t)(ncols * rows * (int)sizeof(C)));
+            for (int a = 0; a < K; ++a)
+                if (s_col[a] >= 0)
+                    osj_bulk_load((uint32_t)__cvta_generic_to_shared(sB + (size_t)a * cs),
+                                  B + (size_t)s_col[a] * ldb + r0, (uint32_t)(rows * (int)sizeof(C)), bar);
+        }
+        osj_mbar_wait(bar, parity);
+        parity ^= 1;
+        __syncthreads(); // the zero fill of missing columns
+    };
+
+    // ---- phase 1: Gram blocks M00, M01, M11 on DMMA; warps split the 4-row k-steps --------------------------------
+    {
+        double g[3][2][CPLX ? 2 : 1]; // [block][d0,d1][re,im]
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int z = 0; z < (CPLX ? 2 : 1); ++z)
+                    g[b][h][z] = 0.0;
+        for (int ch = 0; ch < nchunks; ++ch)
+        {
+            const int r0 = ch * rpc, rows = min(rpc, ldb - r0);
+            if (ch > 0)
+                __syncthreads();
+            load_chunk(r0, rows);
+            const C* p0 = sB + (size_t)lc * cs + lq;
+            const C* p1 = sB + (size_t)(8 + lc) * cs + lq;
+            for (int r = 4 * warp; r < rows; r += 32)
+            {
+                const C a0 = p0[r], a1 = p1[r];
+                if constexpr (!CPLX)
+                {
+                    dmma884(g[0][0][0], g[0][1][0], a0, a0);
+                    dmma884(g[1][0][0], g[1][1][0], a0, a1);
+                    dmma884(g[2][0][0], g[2][1][0], a1, a1);
+                }
+                else
+                {
+                    // conj(x) y = (xr yr + xi yi) + i (xr yi - xi yr)
+                    auto blk = [&](int b, const C& x, const C& y)
+                    {
+                        dmma884(g[b][0][0], g[b][1][0], x.re, y.re);
+                        dmma884(g[b][0][0], g[b][1][0], x.im, y.im);
+                        dmma884(g[b][0][1], g[b][1][1], x.re, y.im);
+                        dmma884(g[b][0][1], g[b][1][1], -x.im, y.re);
+                    };
+                    blk(0, a0, a0);
+                    blk(1, a0, a1);
+                    blk(2, a1, a1);
+                }
+            }
+        }
+        // per-warp partials -> sRed[warp][block][lc*8 + 2*lq + h]
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+                C v;
+                if constexpr (!CPLX)
+                    v = g[b][h][0];
+                else
+                    v = cxd{g[b][h][0], g[b][h][1]};
+                sRed[(warp * 3 + b) * 64 + lc * 8 + 2 * lq + h] = v;
+            }
+        __syncthreads();
+        if (tid < 192)
+        {
+            const int b = tid / 64, e = tid % 64, i = e / 8, j = e % 8;
+            C v = sRed[(0 * 3 + b) * 64 + e];
+#pragma unroll
+            for (int w = 1; w < 8; ++w)
+                v = cadd(v, sRed[(w * 3 + b) * 64 + e]);
+            if (b == 0)
+                sM[i][j] = v;
+            else if (b == 2)
+                sM[8 + i][8 + j] = v;
+            else
+            {
+                sM[i][8 + j] = v;
+                sM[8 + j][i] = cconj(v);
+            }
+        }
+    }
+    // J = I
+    {
+        const int i = tid / K, j = tid % K;
+        sJ[i][j] = (i == j) ? from_real<C>(1.0) : czero<C>();
+    }
+    __syncthreads();
+
+    // ---- convergence test on the fresh Gram matrix --------------------------------------------------------
+    {
+        const int i = tid / K, j = tid % K;
+        if (i < j)
+        {
+            const double a = creal(sM[i][i]), b = creal(sM[j][j]);
+            const double gg = sqrt(cabs2(sM[i][j]));
+            if (a > 0.0 && b > 0.0)
+            {
+                const double ratio = gg / sqrt(a * b);
+                if (ratio > tol)
+                {
+                    s_active = 1; // benign race
+                    atomicMax(maxoff_bits, (unsigned long long)__double_as_longlong(ratio));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!s_active)
+        return;
+    if (tid == 0)
+        atomicAdd(nrot, 1);
+
+    // ---- phase 2: one cyclic sweep on M in shared memory (15 steps of 8 disjoint pairs), J accumulated ----
+    for (int step = 0; step < K - 1; ++step)
+    {
+        if (tid < K / 2)
+        {
+            int p, q;
+            rr_pair(step, tid, K, p, q);
+            if (p > q)
+            {
+                const int t = p;
+                p = q;
+                q = t;
+            }
+            const double a = creal(sM[p][p]), b = creal(sM[q][q]);
+            const C gpq = sM[p][q];
+            const double thresh = (a > 0.0 && b > 0.0) ? tol * sqrt(a * b) : 1e300;
+            sR[tid] = make_rot<C>(a, b, gpq, thresh);
+        }
+        __syncthreads();
+        if (tid < (K / 2) * (K / 2))
+        {
+            const int ia = tid / (K / 2), ib = tid % (K / 2);
+            int pa, qa, pb, qb;
+            rr_pair(step, ia, K, pa, qa);
+            rr_pair(step, ib, K, pb, qb);
+            if (pa > qa)
+            {
+                const int t = pa;
+                pa = qa;
+                qa = t;
+            }
+            if (pb > qb)
+            {
+                const int t = pb;
+                pb = qb;
+                qb = t;
+            }
+            const JRot Ra = sR[ia], Rb = sR[ib];
+            if (Ra.active || Rb.active)
+            {
+                C b00 = sM[pa][pb], b01 = sM[pa][qb], b10 = sM[qa][pb], b11 = sM[qa][qb];
+                rot_block<C>(b00, b01, b10, b11, Ra, Rb);
+                if (ia == ib)
+                {
+                    b00 = real_only(b00);
+                    b11 = real_only(b11);
+                    b01 = czero<C>();
+                    b10 = czero<C>();
+                }
+                sM[pa][pb] = b00;
+                sM[pa][qb] = b01;
+                sM[qa][pb] = b10;
+                sM[qa][qb] = b11;
+            }
+        }
+        else if (tid >= 128 && tid < 128 + K * (K / 2))
+        {
+            const int t = tid - 128;
+            const int i = t / (K / 2), ib = t % (K / 2);
+            int pb, qb;
+            rr_pair(step, ib, K, pb, qb);
+            if (pb > qb)
+            {
+                const int tt = pb;
+                pb = qb;
+                qb = tt;
+            }
+            const JRot Rb = sR[ib];
+            if (Rb.active)
+            {
+                const C ub = cconj(load_u<C>(Rb));
+                const C x = sJ[i][pb], y = sJ[i][qb];
+                sJ[i][pb] = csub(cmul(Rb.c, x), cmul(Rb.s, cmul(ub, y)));
+                sJ[i][qb] = cadd(cmul(Rb.s, x), cmul(Rb.c, cmul(ub, y)));
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3: Bp <- Bp J on DMMA; warp w owns the 8-row blocks w, w + 8, ... ---------------------------------
+    C jf[4][2]; // J fragments: B operand of (k-step a, column block jb): J[4a + lq][8jb + lc]
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int jb = 0; jb < 2; ++jb)
+            jf[a][jb] = sJ[4 * a + lq][8 * jb + lc];
+    for (int ch = 0; ch < nchunks; ++ch)
+    {
+        const int r0 = ch * rpc, rows = min(rpc, ldb - r0);
+        if (nchunks > 1)
+        {
+            __syncthreads();
+            load_chunk(r0, rows);
+        }
+        for (int r = 8 * warp; r < rows; r += 64)
+        {
+            // A fragments: X[r + lc][4a + lq]; rows beyond the chunk (rows is a multiple of 4, not of 8) read as zero
+            const bool in = r + lc < rows;
+            C xf[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                xf[a] = in ? sB[(size_t)(4 * a + lq) * cs + r + lc] : czero<C>();
+            double y[2][2][CPLX ? 2 : 1];
+#pragma unroll
+            for (int jb = 0; jb < 2; ++jb)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int z = 0; z < (CPLX ? 2 : 1); ++z)
+                        y[jb][h][z] = 0.0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int jb = 0; jb < 2; ++jb)
+                {
+                    if constexpr (!CPLX)
+                        dmma884(y[jb][0][0], y[jb][1][0], xf[a], jf[a][jb]);
+                    else
+                    {
+                        dmma884(y[jb][0][0], y[jb][1][0], xf[a].re, jf[a][jb].re);
+                        dmma884(y[jb][0][0], y[jb][1][0], -xf[a].im, jf[a][jb].im);
+                        dmma884(y[jb][0][1], y[jb][1][1], xf[a].re, jf[a][jb].im);
+                        dmma884(y[jb][0][1], y[jb][1][1], xf[a].im, jf[a][jb].re);
+                    }
+                }
+            __syncwarp(); // every lane has read its fragments of these 8 rows
+            if (in)
+            {
+#pragma unroll
+                for (int jb = 0; jb < 2; ++jb)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                    {
+                        C v;
+                        if constexpr (!CPLX)
+                            v = y[jb][h][0];
+                        else
+                            v = cxd{y[jb][h][0], y[jb][h][1]};
+                        sB[(size_t)(8 * jb + 2 * lq + h) * cs + r + lc] = v;
+                    }
+            }
+        }
+        // shared memory -> global with TMA bulk stores (the generic-proxy writes above must be visible to it)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (int a = 0; a < K; ++a)
+                if (s_col[a] >= 0)
+                    osj_bulk_store(B + (size_t)s_col[a] * ldb + r0, (uint32_t)__cvta_generic_to_shared(sB + (size_t)a * cs),
+                                   (uint32_t)(rows * (int)sizeof(C)));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the tile is re-used by the next chunk / released at exit: wait until the stores have READ it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+    // tid 0 has waited until the bulk stores have read the tile (wait_group.read above); the writes themselves are
+    // ordered before the next kernel of the stream by the kernel boundary
+}
+
 // U[:, j] <- B[:, j] / ||B[:, j]||
 template <class C>
 __global__ void __launch_bounds__(256) osj_normalize_kernel(int n, int ldb, C* B)

@@ -287,6 +287,13 @@ using PC = Dist<std::complex<float>>;
 using PZP = Dist<std::complex<double>, chase::matrix::PseudoHermitianMatrix<std::complex<double>, chase::platform::GPU>>;
 using PCP = Dist<std::complex<float>, chase::matrix::PseudoHermitianMatrix<std::complex<float>, chase::platform::GPU>>;
 
+// Fortran callers hold their communicator as an INTEGER: index + 1 into this table (see chase_b200_comm_c2f)
+inline std::vector<void*>& fortran_comm_table()
+{
+    static std::vector<void*> t;
+    return t;
+}
+
 template <class F>
 void with_active_config(F&& f)
 {
@@ -573,6 +580,37 @@ extern "C"
                     chase_b200_version());
     }
 
+    // ---- Fortran twins (reference chase_c_interface.cpp:2296-2327, 2425-2900: the `_f_` entry points the Fortran
+    // module binds to).  A Fortran caller holds its communicator as an INTEGER (MPI_Fint); here that integer is an
+    // index into a table of the handles made by chase_b200_comm_init (chase_b200_comm_c2f / _f2c play the role of
+    // MPI_Comm_c2f / MPI_Comm_f2c).
+    int chase_b200_comm_c2f(void* comm)
+    {
+        auto& tab = fortran_comm_table();
+        for (std::size_t i = 0; i < tab.size(); ++i)
+            if (tab[i] == comm)
+                return (int)i + 1;
+        tab.push_back(comm);
+        return (int)tab.size();
+    }
+    void* chase_b200_comm_f2c(int fcomm)
+    {
+        auto& tab = fortran_comm_table();
+        return (fcomm >= 1 && (std::size_t)fcomm <= tab.size()) ? tab[(std::size_t)fcomm - 1] : nullptr;
+    }
+    void cchase_init_pseudo_f_(int* N, int* nev, int* nex, CHASE_B200_CF* H, int* ldh, CHASE_B200_CF* V, float* ritzv,
+                               int* init)
+    {
+        cchase_init_pseudo_(N, nev, nex, H, ldh, V, ritzv, init);
+    }
+    void zchase_init_pseudo_f_(int* N, int* nev, int* nex, CHASE_B200_CD* H, int* ldh, CHASE_B200_CD* V, double* ritzv,
+                               int* init)
+    {
+        zchase_init_pseudo_(N, nev, nex, H, ldh, V, ritzv, init);
+    }
+    void cchase_pseudo_f_(int* deg, float* tol, char* mode, char* opt, char* qr) { cchase_pseudo_(deg, tol, mode, opt, qr); }
+    void zchase_pseudo_f_(int* deg, double* tol, char* mode, char* opt, char* qr) { zchase_pseudo_(deg, tol, mode, opt, qr); }
+
     // ---- distributed entry points (reference chase_c_interface.h:61-195) ---------------------------------
 #define CB2_DIST_INIT_API(X, PSEUDO, TT, CT, RT, SINGLETON)                                                            \
     void p##X##chase_init_##PSEUDO(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, CT* V, RT* ritzv, int* dim0,  \
@@ -613,6 +651,34 @@ extern "C"
         (void)icsrc;                                                                                                   \
         *init = SINGLETON::get().init(*N, *nev, *nex, *mbsize, *nbsize, reinterpret_cast<TT*>(H), *ldh, nullptr,      \
                                       nullptr, *dim0, *dim1, *grid_major, comm ? *comm : nullptr);                     \
+    }                                                                                                                  \
+    void p##X##chase_init_##PSEUDO##f_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, CT* V, RT* ritzv,  \
+                                       int* dim0, int* dim1, char* grid_major, int* fcomm, int* init)                  \
+    {                                                                                                                  \
+        MPI_Comm c = chase_b200_comm_f2c(*fcomm);                                                                      \
+        p##X##chase_init_##PSEUDO(N, nev, nex, m, n, H, ldh, V, ritzv, dim0, dim1, grid_major, &c, init);              \
+    }                                                                                                                  \
+    void p##X##chase_init_##PSEUDO##internal_f_(int* N, int* nev, int* nex, int* m, int* n, CT* H, int* ldh, int* dim0,\
+                                                int* dim1, char* grid_major, int* fcomm, int* init)                    \
+    {                                                                                                                  \
+        MPI_Comm c = chase_b200_comm_f2c(*fcomm);                                                                      \
+        p##X##chase_init_##PSEUDO##internal_(N, nev, nex, m, n, H, ldh, dim0, dim1, grid_major, &c, init);             \
+    }                                                                                                                  \
+    void p##X##chase_init_##PSEUDO##blockcyclic_f_(int* N, int* nev, int* nex, int* mbsize, int* nbsize, CT* H,        \
+                                                   int* ldh, CT* V, RT* ritzv, int* dim0, int* dim1, char* grid_major, \
+                                                   int* irsrc, int* icsrc, int* fcomm, int* init)                      \
+    {                                                                                                                  \
+        MPI_Comm c = chase_b200_comm_f2c(*fcomm);                                                                      \
+        p##X##chase_init_##PSEUDO##blockcyclic_(N, nev, nex, mbsize, nbsize, H, ldh, V, ritzv, dim0, dim1, grid_major, \
+                                                irsrc, icsrc, &c, init);                                               \
+    }                                                                                                                  \
+    void p##X##chase_init_##PSEUDO##blockcyclic_internal_f_(int* N, int* nev, int* nex, int* mbsize, int* nbsize,      \
+                                                            CT* H, int* ldh, int* dim0, int* dim1, char* grid_major,   \
+                                                            int* irsrc, int* icsrc, int* fcomm, int* init)             \
+    {                                                                                                                  \
+        MPI_Comm c = chase_b200_comm_f2c(*fcomm);                                                                      \
+        p##X##chase_init_##PSEUDO##blockcyclic_internal_(N, nev, nex, mbsize, nbsize, H, ldh, dim0, dim1, grid_major,  \
+                                                         irsrc, icsrc, &c, init);                                      \
     }
 #define CB2_DIST_RUN_API(X, TT, CT, RT, SINGLETON)                                                                     \
     void p##X##chase_(int* deg, RT* tol, char* mode, char* opt, char* qr)                                              \

@@ -49,6 +49,11 @@ extern "C"
        read the host matrix pointer (which may then be NULL at init).  For matrices that must never exist on the host
        (BASELINE config C4: 28.8 GB per GPU). */
     int chase_b200_dist_load_device_matrix_(char* type, const void* src_dev, long long* ld_src);
+    /* Fortran callers hold the communicator as an INTEGER (the reference's MPI_Fint arguments of the `_f_` entry points,
+       chase_c_interface.cpp:2425-2900): chase_b200_comm_c2f registers the handle and returns its index (>= 1),
+       chase_b200_comm_f2c maps it back (NULL if unknown).  Counterparts of MPI_Comm_c2f / MPI_Comm_f2c. */
+    int chase_b200_comm_c2f(void* comm);
+    void* chase_b200_comm_f2c(int fcomm);
     /* grid coordinates of `rank` in a dim0 x dim1 grid with 'R'ow- or 'C'olumn-major rank order */
     int chase_b200_grid_coords(int dim0, int dim1, char grid_major, int rank, int* row_out, int* col_out);
 
