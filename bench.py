@@ -370,6 +370,25 @@ def ours(a):
                "filtered_vecs": rs2[-1].filtered_vecs,
                "start_vectors": "device Philox RNG, regenerated inside every timed step (the reference GPU backend "
                                 "regenerates with cuRAND every solve); nothing is cached between steps"}
+    # ---- extra: the mixed-precision filter (reference option ENABLE_MIXED_PRECISION, off by default there and here) ----
+    mixed = None
+    if not a.no_extras:
+        flag("chase_b200_set_device_rng_", 1)
+        flag("chase_b200_set_matrix_resident_", 1)
+        flag("chase_b200_set_mixed_precision_", 1)
+        try:
+            solver.solve(deg=20, tol=tol, copy=False)
+            rs3, secs3, _ = timed(min(a.steps, 3))
+            L.chase_b200_last_sp_filter_cols_.restype = ctypes.c_double
+            mixed = {"what": "same workload with chase_b200_set_mixed_precision_(1): filters run in single precision on the "
+                             "tcgen05 kind::tf32 kernel while min residual > 1e-3 (reference: ENABLE_MIXED_PRECISION)",
+                     "time_to_solution_s": secs3 / len(rs3), "iterations": rs3[-1].iterations,
+                     "filtered_vecs": rs3[-1].filtered_vecs, "sp_filter_cols": L.chase_b200_last_sp_filter_cols_(),
+                     "value": sum(r.stats["gflop_filter"] for r in rs3) * 1e9 / secs3 / 1e12, "unit": "TFLOP/s",
+                     "phases_s": {k[2:]: rs3[-1].stats[k] for k in ("t_all", "t_filter", "t_qr", "t_rr")},
+                     "max_rel_eig_err": max(check(r) for r in rs3)}
+        finally:
+            flag("chase_b200_set_mixed_precision_", 0)
     solver.finalize()
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
@@ -408,6 +427,8 @@ def ours(a):
             # same box, same workload, host buffers on both sides: the like-for-like speed-up of the drop-in
             line["e2e_vs_gpu_reference"] = g["time_to_solution_s"] / e2e["time_to_solution_s"]
             line["filter_vs_gpu_reference"] = g["phases_s"]["filter"] / st["t_filter"]
+    if mixed:
+        line["mixed_precision"] = mixed
     if not a.no_extras and a.workload == "c2":
         # the fixed complex problem of the multi-GPU arm, on the 1x1 grid of the distributed backend
         from chase_b200 import bench_dist

@@ -38,6 +38,7 @@ def lib():
         _lib.chase_b200_heev_ws_bytes.argtypes = [ctypes.c_int64, ctypes.c_int]
         _lib.chase_b200_hemm_tf32_scratch_bytes.restype = ctypes.c_size_t
         _lib.chase_b200_hemm_tf32_scratch_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+        _lib.chase_b200_last_sp_filter_cols_.restype = ctypes.c_double
         _lib.chase_b200_launch_count.restype = ctypes.c_ulonglong
         _lib.chase_b200_trace_copy_.restype = ctypes.c_size_t
         _lib.chase_b200_trace_copy_.argtypes = [ctypes.c_char_p, ctypes.c_size_t]

@@ -675,8 +675,24 @@ int gemv_impl(int64_t rows, int64_t cols, const void* A, int64_t lda, const void
     cudaStream_t st = S(stream);
     if (rows <= 0 || cols <= 0 || nv <= 0)
         return 0;
-    // one warp per GEMV_CJ columns, 8 warps per block
-    const int blocks = (int)std::min<int64_t>((cols + 8 * GEMV_CJ - 1) / (8 * GEMV_CJ), 148 * 8);
+    // one warp per GEMV_CJ columns, 8 warps per block.  All blocks are resident at once (2 per SM at 128 registers);
+    // the group count per warp is made equal so that no warp walks one column group more than the others
+    int blocks;
+    {
+        const int64_t ngroups = (cols + GEMV_CJ - 1) / GEMV_CJ;
+        const int64_t max_warps = 148 * 2 * 8;
+        const int64_t per_warp = (ngroups + max_warps - 1) / max_warps;
+        const int64_t warps = (ngroups + per_warp - 1) / per_warp;
+        blocks = (int)std::max<int64_t>((warps + 7) / 8, 1);
+    }
+    // 16-byte loads when every column of A and X starts on a 16-byte boundary (CHASE_B200_GEMV_VEC=0: scalar loads)
+    constexpr int64_t VEC = 16 / (int64_t)sizeof(T) > 0 ? 16 / (int64_t)sizeof(T) : 1;
+    static const bool vec_on = []
+    {
+        const char* e = getenv("CHASE_B200_GEMV_VEC");
+        return !(e && atoi(e) == 0);
+    }();
+    const bool vec = vec_on && lda % VEC == 0 && ldx % VEC == 0 && (((uintptr_t)A | (uintptr_t)X) & 15) == 0;
     int v = 0;
     while (v < nv)
     {
@@ -684,7 +700,10 @@ int gemv_impl(int64_t rows, int64_t cols, const void* A, int64_t lda, const void
         T* y = (T*)Y + (int64_t)v * ldy;
         if (nv - v >= 4)
         {
-            gemv_conjT_kernel<T, 4><<<blocks, 256, 0, kcount(st)>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
+            if (vec)
+                gemv_conjT_vec_kernel<T, 4><<<blocks, 256, 0, kcount(st)>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
+            else
+                gemv_conjT_kernel<T, 4><<<blocks, 256, 0, kcount(st)>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
             v += 4;
         }
         else if (nv - v >= 2)
@@ -789,6 +808,22 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
         if (rows <= 0 || cols <= 0)                                                                                    \
             return 0;                                                                                                  \
         lacpy_kernel<TT><<<grid2d(rows, cols), 256, 0, kcount(S(st))>>>(rows, cols, (const TT*)src, lds, (TT*)dst, ldd);      \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_tri_pack_##X(int64_t n, const void* G, int64_t ldg, void* P, int lower, void* st)       \
+    {                                                                                                                  \
+        if (n <= 0)                                                                                                    \
+            return 0;                                                                                                  \
+        tri_pack_kernel<TT, true><<<grid2d(n, n), 256, 0, kcount(S(st))>>>(n, (TT*)const_cast<void*>(G), ldg, (TT*)P, lower); \
+        CB2_CUDA_OK(cudaGetLastError());                                                                               \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    extern "C" int chase_b200_tri_unpack_##X(int64_t n, const void* P, void* G, int64_t ldg, int lower, void* st)     \
+    {                                                                                                                  \
+        if (n <= 0)                                                                                                    \
+            return 0;                                                                                                  \
+        tri_pack_kernel<TT, false><<<grid2d(n, n), 256, 0, kcount(S(st))>>>(n, (TT*)G, ldg, (TT*)const_cast<void*>(P), lower); \
         CB2_CUDA_OK(cudaGetLastError());                                                                               \
         return 0;                                                                                                      \
     }                                                                                                                  \
@@ -1008,6 +1043,27 @@ extern "C" int chase_b200_widen_sync(char type, const void* A, void* stream)
     else if (type == 'c')
         convert_kernel<cxf, cxd><<<grid2d(w.rows, w.cols), 256, 0, kcount(st)>>>(w.rows, w.cols, (const cxf*)A, w.ld,
                                                                                  (cxd*)w.wide, w.ld);
+    else
+        return -2;
+    CB2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// precision change of a rows x cols column-major array: (from, to) in {d->s, s->d, z->c, c->z}
+extern "C" int chase_b200_convert(char from, char to, int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst,
+                                  int64_t ldd, void* stream)
+{
+    if (rows <= 0 || cols <= 0)
+        return 0;
+    cudaStream_t st = S(stream);
+    if (from == 'd' && to == 's')
+        convert_kernel<double, float><<<grid2d(rows, cols), 256, 0, kcount(st)>>>(rows, cols, (const double*)src, lds, (float*)dst, ldd);
+    else if (from == 's' && to == 'd')
+        convert_kernel<float, double><<<grid2d(rows, cols), 256, 0, kcount(st)>>>(rows, cols, (const float*)src, lds, (double*)dst, ldd);
+    else if (from == 'z' && to == 'c')
+        convert_kernel<cxd, cxf><<<grid2d(rows, cols), 256, 0, kcount(st)>>>(rows, cols, (const cxd*)src, lds, (cxf*)dst, ldd);
+    else if (from == 'c' && to == 'z')
+        convert_kernel<cxf, cxd><<<grid2d(rows, cols), 256, 0, kcount(st)>>>(rows, cols, (const cxf*)src, lds, (cxd*)dst, ldd);
     else
         return -2;
     CB2_CUDA_OK(cudaGetLastError());

@@ -37,6 +37,8 @@ LastRun g_last;
 bool g_trace = false;
 int g_matrix_resident = 0; // chase_b200_set_matrix_resident_
 int g_device_rng = -1;     // chase_b200_set_device_rng_ (-1: leave the backend's default / env)
+int g_mixed = -1;          // chase_b200_set_mixed_precision_ (-1: leave the backend's default / env)
+double g_last_sp_cols = 0; // columns the last solve filtered in single precision
 
 // shared by the sequential and the distributed entry points (reference chase_c_interface.cpp:443-491)
 template <class T, class Backend>
@@ -53,6 +55,8 @@ void run_solve(Backend* solver, std::size_t N, int deg, chase::Base<T> tol, char
     solver->keep_device_matrix(g_matrix_resident != 0);
     if (g_device_rng >= 0)
         solver->use_device_rng(g_device_rng != 0);
+    if (g_mixed >= 0)
+        solver->use_mixed_precision(g_mixed != 0);
     chase::PerformanceDecoratorChase<T> perf(solver);
     perf.EnableTrace(g_trace);
     g_last.error.clear();
@@ -93,6 +97,7 @@ void run_solve(Backend* solver, std::size_t N, int deg, chase::Base<T> tol, char
     s[13] = (double)solver->heev_sweeps();
     s[14] = (double)solver->gather_passes();
     s[15] = g_last.error.empty() ? 0.0 : 1.0;
+    g_last_sp_cols = (double)solver->sp_filter_cols();
     g_last.trace.clear();
     for (auto& l : perf.Trace())
     {
@@ -954,6 +959,8 @@ extern "C"
     void chase_b200_trace_enable_(int* flag) { g_trace = (*flag != 0); }
     void chase_b200_set_matrix_resident_(int* flag) { g_matrix_resident = *flag; }
     void chase_b200_set_device_rng_(int* flag) { g_device_rng = *flag; }
+    void chase_b200_set_mixed_precision_(int* flag) { g_mixed = *flag; }
+    double chase_b200_last_sp_filter_cols_(void) { return g_last_sp_cols; }
     size_t chase_b200_trace_copy_(char* buf, size_t cap) { return copy_out(g_last.trace, buf, cap); }
     size_t chase_b200_qr_log_copy_(char* buf, size_t cap) { return copy_out(g_last.qr_log, buf, cap); }
     size_t chase_b200_last_error_copy_(char* buf, size_t cap) { return copy_out(g_last.error, buf, cap); }

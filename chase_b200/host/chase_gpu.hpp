@@ -137,6 +137,8 @@ public:
             perm_[i] = (int)i;
         const char* e = std::getenv("CHASE_B200_DEVICE_RNG");
         device_rng_ = e && std::atoi(e) != 0;
+        const char* mp = std::getenv("CHASE_B200_MIXED_PRECISION");
+        mixed_ = mp && std::atoi(mp) != 0;
         // FP32 storage.  Default: the tcgen05 kind::tf32 kernel with 3x/4x TF32 splitting (csrc/hemm_tf32.cuh): the
         // matrix as stored is the hi operand, one extra FP32 array holds the lo part (2x the matrix memory).
         // CHASE_B200_FP32_PATH=fp64copy: the round-1 route through an FP64 copy on the DMMA kernel (3x memory);
@@ -230,6 +232,7 @@ public:
             CB2_CHECK(cudaMemcpy2DAsync(dH_, ld_ * sizeof(T), H_, ldh_ * sizeof(T), N_ * sizeof(T), N_,
                                         cudaMemcpyHostToDevice, stream_));
             matrix_on_device_ = true;
+            sp_matrix_valid_ = false;
             if (dHw_)
                 CB2_KCHECK(chase_b200_widen_sync(kCplx ? 'c' : 's', dH_, stream_));
             if (dHl_)
@@ -239,14 +242,52 @@ public:
         shift_ = 0.0;
     }
 
-    void Shift(T c, bool /*isunshift*/ = false) override { shift_ += (double)std::real(c); }
+    // A stays immutable: the shift is folded into the HEMM epilogue.  Shift(-c) / Shift(+c, true) also bracket the
+    // filter, which is where the reference switches its mixed-precision mode on and off (ENABLE_MIXED_PRECISION,
+    // Impl/pchase_gpu/pchase_gpu.hpp:785-817): while the smallest residual of the wanted, unlocked pairs is above
+    // 1e-3 the filter of a double-precision problem runs in single precision -- here on the tcgen05 kind::tf32
+    // kernel (FP32-accurate 3xTF32) -- and the filtered block is converted back at the unshift.  Opt-in like the
+    // reference's compile-time option: CHASE_B200_MIXED_PRECISION=1 or chase_b200_set_mixed_precision_.
+    void Shift(T c, bool isunshift = false) override
+    {
+        shift_ += (double)std::real(c);
+        if constexpr (sizeof(R) == 8 && !kPseudo)
+        {
+            if (!mixed_)
+                return;
+            if (!isunshift)
+            {
+                R mn = std::numeric_limits<R>::max();
+                for (std::size_t i = locked_; i < nev_; ++i)
+                    mn = std::min(mn, resid_[i]);
+                if (locked_ < nev_ && mn > R(1e-3))
+                    sp_begin();
+            }
+            else if (sp_active_)
+                sp_end();
+        }
+    }
 
     void HEMM(std::size_t block, T alpha, T beta, std::size_t offset_left, std::size_t offset_right = 0) override
     {
         flush_perm();
         resid_ready_ = false;
         const std::size_t ncols = (offset_right < block) ? block - offset_right : 0;
-        if (ncols > 0)
+        if (ncols > 0 && sp_active_)
+        {
+            const std::size_t c0 = offset_left + locked_;
+            const std::size_t es = sizeof(T) / 2; // bytes of the single-precision element
+            auto fn = kCplx ? chase_b200_hemm_tf32_c : chase_b200_hemm_tf32_s;
+            const int rc = fn((int64_t)N_, (int64_t)N_, (int64_t)ncols, b200::re_of(alpha), b200::im_of(alpha), dHs_, dHsl_,
+                              (int64_t)ld_, dV1s_ + c0 * ld_ * es, (int64_t)ld_, b200::re_of(beta), b200::im_of(beta),
+                              dV2s_ + c0 * ld_ * es, (int64_t)ld_, -shift_, nullptr, 0, 3, sp_scratch_, sp_scratch_bytes_,
+                              stream_);
+            CB2_KCHECK(rc);
+            hemm_cols_ += ncols;
+            sp_cols_ += ncols;
+            std::swap(dV1s_, dV2s_);
+        }
+        else if (ncols > 0)
         {
             const std::size_t c0 = offset_left + locked_;
             // A_eff = A + shift_ I  ->  alpha (A - (-shift_) I) B + beta C
@@ -644,9 +685,14 @@ public:
         hemm_cols_ = 0;
         swaps_ = 0;
         gathers_ = 0;
+        sp_cols_ = 0;
+        sp_filters_ = 0;
     }
     void keep_device_matrix(bool f) { keep_device_matrix_ = f; }
     void use_device_rng(bool f) { device_rng_ = f; }
+    void use_mixed_precision(bool f) { mixed_ = f; }
+    std::size_t sp_filter_cols() const { return sp_cols_; } // columns filtered in single precision
+    std::size_t sp_filters() const { return sp_filters_; }
     std::size_t heev_sweeps() const { return heev_sweeps_; }
     std::size_t hemm_cols() const { return hemm_cols_; } // columns actually multiplied by the filter
     std::size_t gather_passes() const { return gathers_; }
@@ -714,6 +760,48 @@ private:
             resid_ready_ = false; // dW_ was the gather scratch
         }
         reset_perm();
+    }
+
+    // ---- mixed-precision filter (double-precision problems only) -----------------------------------------------
+    void sp_begin()
+    {
+        const std::size_t es = sizeof(T) / 2;
+        const char wide = kCplx ? 'z' : 'd', narrow = kCplx ? 'c' : 's';
+        if (dHs_ == nullptr)
+        {
+            dHs_ = alloc<unsigned char>(ld_ * N_ * es);
+            dHsl_ = alloc<unsigned char>(ld_ * N_ * es);
+            dV1s_ = alloc<unsigned char>(ld_ * nc_ * es);
+            dV2s_ = alloc<unsigned char>(ld_ * nc_ * es);
+            sp_scratch_bytes_ = chase_b200_hemm_tf32_scratch_bytes((int64_t)N_, (int64_t)nc_, (int)es);
+            sp_scratch_ = alloc<unsigned char>(sp_scratch_bytes_);
+        }
+        if (!sp_matrix_valid_)
+        {
+            // single-precision copy of A + the lo part of its TF32 split, once per upload of the matrix
+            CB2_KCHECK(chase_b200_convert(wide, narrow, (int64_t)N_, (int64_t)N_, dH_, (int64_t)ld_, dHs_, (int64_t)ld_,
+                                          stream_));
+            CB2_KCHECK(chase_b200_tf32_register(dHs_, dHsl_, (int64_t)ld_, (int64_t)N_, (int64_t)N_, 0, nullptr, 0));
+            CB2_KCHECK(chase_b200_tf32_sync(narrow, dHs_, stream_));
+            chase_b200_tf32_unregister(dHs_);
+            sp_matrix_valid_ = true;
+        }
+        flush_perm();
+        const std::size_t act = nevex_ - locked_;
+        CB2_KCHECK(chase_b200_convert(wide, narrow, (int64_t)N_, (int64_t)act, dV1_ + locked_ * ld_, (int64_t)ld_,
+                                      dV1s_ + locked_ * ld_ * es, (int64_t)ld_, stream_));
+        sp_active_ = true;
+        sp_filters_++;
+    }
+    // the filtered block (every degree is even, so it sits in the primary panel) goes back to double precision
+    void sp_end()
+    {
+        const std::size_t es = sizeof(T) / 2;
+        const std::size_t act = nevex_ - locked_;
+        CB2_KCHECK(chase_b200_convert(kCplx ? 'c' : 's', kCplx ? 'z' : 'd', (int64_t)N_, (int64_t)act,
+                                      dV1s_ + locked_ * ld_ * es, (int64_t)ld_, dV1_ + locked_ * ld_, (int64_t)ld_,
+                                      stream_));
+        sp_active_ = false;
     }
 
     // one CholQR round on all nev+nex columns; shift_boost > 0 adds the shifted-CholQR shift
@@ -996,6 +1084,10 @@ private:
     unsigned char *dHw_ = nullptr, *wide_scratch_ = nullptr; // FP64 copy of an FP32 matrix + panel scratch
     std::size_t wide_scratch_bytes_ = 0;
     T* dHl_ = nullptr; // lo part of the TF32 split of an FP32 matrix (tcgen05 path)
+    // mixed-precision filter of a double-precision problem: single-precision A (+ lo part), two panels, scratch
+    unsigned char *dHs_ = nullptr, *dHsl_ = nullptr, *dV1s_ = nullptr, *dV2s_ = nullptr, *sp_scratch_ = nullptr;
+    std::size_t sp_scratch_bytes_ = 0, sp_cols_ = 0, sp_filters_ = 0;
+    bool mixed_ = false, sp_active_ = false, sp_matrix_valid_ = false;
     unsigned char* tf32_scratch_ = nullptr;
     std::size_t tf32_scratch_bytes_ = 0;
     double* ones_ = nullptr;

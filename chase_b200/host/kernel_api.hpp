@@ -31,6 +31,8 @@ struct K;
         static constexpr auto heev = chase_b200_heev_##X;                                                              \
         static constexpr auto colnorms = chase_b200_colnorms_##X;                                                      \
         static constexpr auto lacpy = chase_b200_lacpy_##X;                                                            \
+        static constexpr auto tri_pack = chase_b200_tri_pack_##X;                                                      \
+        static constexpr auto tri_unpack = chase_b200_tri_unpack_##X;                                                  \
         static constexpr auto gather_cols = chase_b200_gather_cols_##X;                                                \
         static constexpr auto gemv_conjt = chase_b200_gemv_conjt_##X;                                                  \
         static constexpr auto lanczos_step = chase_b200_lanczos_step_##X;                                              \

@@ -392,10 +392,7 @@ public:
         // G = W2^H W1 summed over the grid row, then made bit-identical everywhere
         CB2_KCHECK(KK::gemm(1, 0, (int64_t)block, (int64_t)block, (int64_t)n_loc_, 1.0, 0.0, W2, (int64_t)ldw_, W1,
                             (int64_t)ldw_, 0.0, 0.0, dG_, (int64_t)ldg_, 0, splitk_ws_, splitk_ws_bytes_, stream_));
-        if (grid_.c > 1)
-            comm_.allreduce_sum(dG_, ldg_ * block, comm_.row(), stream_);
-        if (grid_.r > 1)
-            comm_.broadcast(dG_, ldg_ * block, 0, comm_.col(), stream_);
+        sum_triangle(dG_, (int64_t)block, true, false); // the eigensolver reads the lower triangle
         std::vector<double> w(block);
         int sweeps = 0;
         int rc = KK::heev((int64_t)block, dG_, (int64_t)ldg_, dZ_, (int64_t)ldg_, w.data(), heev_ws_, heev_ws_bytes_,
@@ -683,6 +680,10 @@ public:
     }
     void keep_device_matrix(bool f) { keep_device_matrix_ = f; }
     void use_device_rng(bool f) { device_rng_ = f; }
+    // the mixed-precision filter (single-precision tcgen05 kernel while the residuals are above 1e-3) is built for
+    // the single-GPU backend; the distributed HEMM needs the M-major operand orientation the kind::tf32 kernel lacks
+    void use_mixed_precision(bool) {}
+    std::size_t sp_filter_cols() const { return 0; }
     std::size_t heev_sweeps() const { return heev_sweeps_; }
     std::size_t hemm_cols() const { return hemm_cols_; } // columns actually multiplied by the filter
     std::size_t gather_passes() const { return gathers_; }
@@ -880,6 +881,27 @@ private:
         }
     } qrt_;
 
+    // Sum of the per-rank contributions to a Hermitian n x n matrix of which only one triangle is needed afterwards
+    // (upper: potrf; lower: heev), made bit-identical on every rank: the packed triangle (n (n+1) / 2 elements, half
+    // the padded square) is all-reduced inside one communicator and broadcast inside the other, like the reference's
+    // extractUpperTriangular + allreduce + unpack (nccl/cholqr.hpp:152-157, nccl/rayleighRitz.hpp:124-132).
+    void sum_triangle(T* G, int64_t n, bool lower, bool reduce_in_col)
+    {
+        const bool red = reduce_in_col ? grid_.r > 1 : grid_.c > 1;
+        const bool bc = reduce_in_col ? grid_.c > 1 : grid_.r > 1;
+        if (!red && !bc)
+            return;
+        const std::size_t cnt = (std::size_t)n * (std::size_t)(n + 1) / 2;
+        if (dPack_ == nullptr)
+            dPack_ = alloc<T>(nc_ * (nc_ + 1) / 2);
+        CB2_KCHECK(KK::tri_pack(n, G, (int64_t)ldg_, dPack_, lower ? 1 : 0, stream_));
+        if (red)
+            comm_.allreduce_sum(dPack_, cnt, reduce_in_col ? comm_.col() : comm_.row(), stream_);
+        if (bc)
+            comm_.broadcast(dPack_, cnt, 0, reduce_in_col ? comm_.row() : comm_.col(), stream_);
+        CB2_KCHECK(KK::tri_unpack(n, dPack_, G, (int64_t)ldg_, lower ? 1 : 0, stream_));
+    }
+
     int chol_round(bool shifted, double shift_boost)
     {
         const int64_t n = (int64_t)nc_;
@@ -887,10 +909,7 @@ private:
         CB2_KCHECK(KK::gemm(1, 0, n, n, (int64_t)m_loc_, 1.0, 0.0, dV1_, (int64_t)ldv_, dV1_, (int64_t)ldv_, 0.0, 0.0,
                             dG_, (int64_t)ldg_, 1, splitk_ws_, splitk_ws_bytes_, stream_));
         qrt_.lap(stream_, 0);
-        if (grid_.r > 1)
-            comm_.allreduce_sum(dG_, ldg_ * nc_, comm_.col(), stream_);
-        if (grid_.c > 1)
-            comm_.broadcast(dG_, ldg_ * nc_, 0, comm_.row(), stream_);
+        sum_triangle(dG_, n, false, true); // potrf reads the upper triangle
         qrt_.lap(stream_, 1);
         if (shifted)
         {
@@ -982,10 +1001,7 @@ private:
         // G = Q^H S H Q
         CB2_KCHECK(KK::gemm(1, 0, n, n, (int64_t)n_loc_, 1.0, 0.0, W2, (int64_t)ldw_, W1, (int64_t)ldw_, 0.0, 0.0, dG_, ldg,
                             0, splitk_ws_, splitk_ws_bytes_, stream_));
-        if (grid_.c > 1)
-            comm_.allreduce_sum(dG_, ldg_ * nn, comm_.row(), stream_);
-        if (grid_.r > 1)
-            comm_.broadcast(dG_, ldg_ * nn, 0, comm_.col(), stream_);
+        sum_triangle(dG_, n, false, false); // factorised by potrf: upper triangle
         // M0 = Q^H S Q (= I - 2 Q2^H Q2 for orthonormal Q)
         CB2_KCHECK(KK::gemm(1, 0, n, n, (int64_t)m_loc_, 1.0, 0.0, Q, (int64_t)ldv_, SQ, (int64_t)ldv_, 0.0, 0.0, dM_, ldg,
                             0, splitk_ws_, splitk_ws_bytes_, stream_));
@@ -1214,6 +1230,7 @@ private:
       *dZ_ = nullptr;
     T* dW_[4] = {nullptr, nullptr, nullptr, nullptr};
     T *dM_ = nullptr, *dRinv_ = nullptr, *dT_ = nullptr, *dFull_ = nullptr; // pseudo-Hermitian only
+    T* dPack_ = nullptr; // packed triangle of a Gram / projected matrix (allreduce payload)
     unsigned char *dHw_ = nullptr, *wide_scratch_ = nullptr; // FP64 copy of an FP32 local block + panel scratch
     std::size_t wide_scratch_bytes_ = 0;
     bool wide_valid_ = false;

@@ -118,6 +118,16 @@ def hemm_tf32(M, K, k, alpha, A, Alo, lda, B, ldb, beta, C, ldc, shift=0.0, thet
     return _chk(rc, "hemm_tf32")
 
 
+def tri_pack(n, G, ldg, P, lower):
+    f = getattr(lib(), f"chase_b200_tri_pack_{_sfx(G)}")
+    return _chk(f(ctypes.c_int64(n), _ptr(G), ctypes.c_int64(ldg), _ptr(P), int(lower), _stream()), "tri_pack")
+
+
+def tri_unpack(n, P, G, ldg, lower):
+    f = getattr(lib(), f"chase_b200_tri_unpack_{_sfx(G)}")
+    return _chk(f(ctypes.c_int64(n), _ptr(P), _ptr(G), ctypes.c_int64(ldg), int(lower), _stream()), "tri_unpack")
+
+
 def potrf(n, G, ldg, info):
     f = getattr(lib(), f"chase_b200_potrf_{_sfx(G)}")
     return _chk(f(ctypes.c_int64(n), _ptr(G), ctypes.c_int64(ldg), _ptr(info), _stream()), "potrf")

@@ -75,6 +75,11 @@ extern "C"
     /* dst <- src (rows x cols).  Replaces cuda::t_lacpy('A') (reference cuda/lacpy.cu:62-496). */                    \
     int chase_b200_lacpy_##X(int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst, int64_t ldd,        \
                              void* stream);                                                                            \
+    /* Packed triangle of the n x n matrix G (LAPACK 'U' / 'L' column-major packing, n (n+1) / 2 elements) and back:  \
+       the payload of the Gram / projected-matrix allreduces.  Replaces cuda::extractUpperTriangular /                \
+       unpackUpperTriangular (reference cuda/lacpy.cu:837-, 956-; nccl/cholqr.hpp:152-157). */                        \
+    int chase_b200_tri_pack_##X(int64_t n, const void* G, int64_t ldg, void* P, int lower, void* stream);             \
+    int chase_b200_tri_unpack_##X(int64_t n, const void* P, void* G, int64_t ldg, int lower, void* stream);           \
     /* dst[:, dcols[t]] <- src[:, scols[t]], t < cnt (index arrays on the device; src != dst).  Batched form of       \
        the reference's per-call cublasTswap (Impl/chase_gpu/chase_gpu.hpp:1000-1006). */                              \
     int chase_b200_gather_cols_##X(int64_t rows, int cnt, const int* scols_dev, const int* dcols_dev,                 \
@@ -193,6 +198,10 @@ extern "C"
     int chase_b200_tf32_unregister(const void* A);
     int chase_b200_tf32_sync(char type, const void* A, void* stream);
     void chase_b200_tf32_set_terms(int terms);
+    /* Precision change of a rows x cols column-major array, (from, to) in {'d'->'s', 's'->'d', 'z'->'c', 'c'->'z'}:
+       the copies behind the mixed-precision filter (reference linalg/internal/cuda/precision_conversion.cu:20-55). */
+    int chase_b200_convert(char from, char to, int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst,
+                           int64_t ldd, void* stream);
     size_t chase_b200_trsm_ws_bytes(int64_t n, int elem_bytes);
     size_t chase_b200_hhqr_ws_bytes(int64_t rows, int64_t n, int elem_bytes);
     size_t chase_b200_heev_ws_bytes(int64_t n, int is_complex);

@@ -197,6 +197,14 @@ extern "C"
        does with cuRAND, chase_gpu.hpp:509-533); 0 (default): the reference CPU backend's mt19937 stream, which is
        what makes iteration counts identical to the reference CPU solver */
     void chase_b200_set_device_rng_(int* flag);
+    /* flag != 0: double-precision problems (d, z; sequential solver) filter in single precision -- on the tcgen05
+       kind::tf32 kernel, FP32-accurate -- while the smallest residual of the wanted, unlocked pairs is above 1e-3, and in
+       double precision afterwards: the reference's compile-time option ENABLE_MIXED_PRECISION
+       (Impl/pchase_gpu/pchase_gpu.hpp:785-881), here a run-time switch (also CHASE_B200_MIXED_PRECISION=1).  Off by
+       default, like the reference: the degree schedule of a mixed-precision run differs from the double-precision one.
+       chase_b200_last_sp_filter_cols_: matrix-vector products the last solve did in single precision. */
+    void chase_b200_set_mixed_precision_(int* flag);
+    double chase_b200_last_sp_filter_cols_(void);
 
 #ifdef __cplusplus
 }

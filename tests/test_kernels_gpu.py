@@ -504,3 +504,27 @@ def test_reference_qr_fixtures(t, name, cond):
     Q = k.to_numpy(dQ, rows).astype(wide)
     orth = np.linalg.norm(Q.conj().T @ Q - np.eye(n)) / np.sqrt(n)
     assert orth < lim * eps
+
+
+@pytest.mark.parametrize("t", ["s", "d", "c", "z"])
+@pytest.mark.parametrize("lower", [0, 1])
+def test_packed_triangle_roundtrip(t, lower):
+    """tri_pack / tri_unpack = LAPACK 'U' / 'L' packed storage (reference cuda/lacpy.cu:837-, 956-): the payload of
+    the distributed Gram allreduce."""
+    k = K()
+    n, ldg = 77, 80
+    rng = np.random.default_rng(5)
+    G = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if t in "cz" else 0)
+    G = G.astype(DT[t])
+    dG = k.colmajor(G, ldg)
+    dP = torch.zeros(n * (n + 1) // 2, dtype=dG.dtype, device="cuda")
+    k.tri_pack(n, dG, ldg, dP, lower)
+    P = dP.cpu().numpy()
+    ref = np.concatenate([G[j:, j] if lower else G[: j + 1, j] for j in range(n)])
+    assert np.array_equal(P, ref)
+    dH = torch.full_like(dG, 9.0)
+    k.tri_unpack(n, dP, dH, ldg, lower)
+    H = k.to_numpy(dH, n)
+    mask = np.tril(np.ones((n, n), bool)) if lower else np.triu(np.ones((n, n), bool))
+    assert np.array_equal(H[mask], G[mask])
+    assert np.all(H[~mask] == 9.0)

@@ -103,3 +103,37 @@ def test_fp32_solves_use_the_tcgen05_kernel():
         assert np.max(np.abs(res.ritzv[:nev] - refv) / np.abs(refv)) < 1e-4
         assert np.all(res.resid[:nev] < 100 * g["tol"])
         assert abs(res.iterations - p["iterations"]) <= 1, (name, res.iterations, p["iterations"])
+
+
+@pytest.mark.parametrize("t", ["d", "z"])
+def test_mixed_precision_filter_reaches_double_precision_results(t):
+    """chase_b200_set_mixed_precision_ (the reference's ENABLE_MIXED_PRECISION, pchase_gpu.hpp:785-881): the first
+    filters of a double-precision problem run in single precision on the tcgen05 kernel (residuals > 1e-3), the rest in
+    double; the converged eigenpairs must be as good as a pure double-precision solve's."""
+    import ctypes
+
+    import chase_b200
+    from oracle import chase_oracle as co
+
+    N, nev, nex = 1500, 80, 40
+    lam = co.uniform_spectrum(N)
+    H = co.dense_from_spectrum(lam, np.float64 if t == "d" else np.complex128)
+    L = chase_b200.lib()
+    with chase_b200.ChASE(H, nev, nex) as s:
+        ref = s.solve()
+        assert L.chase_b200_last_sp_filter_cols_() == 0
+        L.chase_b200_set_mixed_precision_(ctypes.byref(ctypes.c_int(1)))
+        try:
+            res = s.solve()
+            sp_cols = L.chase_b200_last_sp_filter_cols_()
+        finally:
+            L.chase_b200_set_mixed_precision_(ctypes.byref(ctypes.c_int(0)))
+        again = s.solve()
+    assert sp_cols >= (nev + nex) * 20  # at least the first filter (degree 20 on every column)
+    assert sp_cols < res.filtered_vecs  # ... and not all of them
+    assert np.max(np.abs(res.ritzv[:nev] - lam[:nev]) / lam[:nev]) < 1e-10
+    assert np.all(res.resid[:nev] < 1e-8)
+    V = res.V[:, :nev]
+    assert np.all(np.linalg.norm(H @ V - V * res.ritzv[:nev], axis=0) < 1e-8)
+    # switching it off again restores the double-precision run bit for bit
+    assert again.filtered_vecs == ref.filtered_vecs and np.array_equal(again.ritzv, ref.ritzv)
