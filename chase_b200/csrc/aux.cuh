@@ -227,12 +227,14 @@ __global__ void __launch_bounds__(256) gemv_conjT_kernel(long long rows, long lo
     }
 }
 
-// Same product with 16-byte loads (2 doubles / 4 floats / 1 complex<double> per lane and request) and two requests
-// per column in flight: a warp that walks its 4 columns with 8-byte loads and a 2-deep unroll keeps 2 KB in flight and
-// is latency-bound (measured 4.5 TB/s = 0.68 of the copy peak at N = 20000: 320 dependent iterations of ~2 us);
-// here it keeps 8 KB in flight.  Needs 16-byte aligned columns (lda, ldx multiples of VEC, aligned bases).
+// Same product, one CTA per group of GEMV_CJ columns: the 8 warps walk the SAME columns side by side with 16-byte
+// loads, so every request wave is 4 KB contiguous per column and two waves are in flight (32 KB per CTA), and the
+// partial sums are added across the warps at the end (fixed order).  Background: with one warp per column group the
+// kernel ran ~6700 concurrent 256/512-byte streams and reached 0.68-0.77 of the copy peak at N = 20000 (DRAM page
+// locality, 300+ dependent iterations per warp); fewer, fatter streams are what the copy benchmark itself does.
+// Needs 16-byte aligned columns (lda, ldx multiples of VEC, aligned bases).
 template <class T, int NV>
-__global__ void __launch_bounds__(256) gemv_conjT_vec_kernel(long long rows, long long cols, const T* A, long long lda,
+__global__ void __launch_bounds__(256) gemv_conjT_blk_kernel(long long rows, long long cols, const T* A, long long lda,
                                                               const T* X, long long ldx, T* Y, long long ldy)
 {
     using C = typename Traits<T>::comp;
@@ -243,12 +245,11 @@ __global__ void __launch_bounds__(256) gemv_conjT_vec_kernel(long long rows, lon
     {
         T v[VEC];
     };
-    const int lane = threadIdx.x & 31;
-    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    __shared__ C sred[8][CJ * NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long ngroups = (cols + CJ - 1) / CJ;
-    const long long step = 32 * VEC;
-    for (long long g = warp; g < ngroups; g += nwarps)
+    const long long wave = 8 * 32 * VEC; // rows covered by one request wave of the CTA
+    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x)
     {
         const long long j0 = g * CJ;
         const T* a[CJ];
@@ -261,20 +262,20 @@ __global__ void __launch_bounds__(256) gemv_conjT_vec_kernel(long long rows, lon
 #pragma unroll
             for (int v = 0; v < NV; ++v)
                 acc[c][v] = czero<C>();
-        long long b = 0; // warp-uniform row base
-        for (; b + U * step <= rows; b += U * step)
+        long long b = 0; // CTA-uniform row base
+        for (; b + U * wave <= rows; b += U * wave)
         {
-            const long long i = b + (long long)lane * VEC;
+            const long long i = b + (long long)(warp * 32 + lane) * VEC;
             Pack av[U][CJ], xv[U][NV];
 #pragma unroll
             for (int u = 0; u < U; ++u)
             {
 #pragma unroll
                 for (int c = 0; c < CJ; ++c)
-                    av[u][c] = *reinterpret_cast<const Pack*>(a[c] + i + u * step);
+                    av[u][c] = *reinterpret_cast<const Pack*>(a[c] + i + u * wave);
 #pragma unroll
                 for (int v = 0; v < NV; ++v)
-                    xv[u][v] = *reinterpret_cast<const Pack*>(X + i + u * step + v * ldx);
+                    xv[u][v] = *reinterpret_cast<const Pack*>(X + i + u * wave + v * ldx);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -289,8 +290,8 @@ __global__ void __launch_bounds__(256) gemv_conjT_vec_kernel(long long rows, lon
                             acc[c][v] = cadd(acc[c][v], cmul(ac, widen(xv[u][v].v[e])));
                     }
         }
-        // remaining rows (< U * step), element by element
-        for (long long r = b + lane; r < rows; r += 32)
+        // remaining rows (< U * wave), element by element
+        for (long long r = b + threadIdx.x; r < rows; r += 256)
         {
             C xs[NV];
 #pragma unroll
@@ -315,9 +316,21 @@ __global__ void __launch_bounds__(256) gemv_conjT_vec_kernel(long long rows, lon
                     r = cxd{warp_sum(acc[c][v].re), warp_sum(acc[c][v].im)};
                 else
                     r = warp_sum(acc[c][v]);
-                if (lane == 0 && j0 + c < cols)
-                    Y[j0 + c + v * ldy] = narrow<T>(r);
+                if (lane == 0)
+                    sred[warp][c * NV + v] = r;
             }
+        __syncthreads();
+        if (threadIdx.x < CJ * NV)
+        {
+            const int c = threadIdx.x / NV, v = threadIdx.x % NV;
+            C r = sred[0][threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < 8; ++w)
+                r = cadd(r, sred[w][threadIdx.x]);
+            if (j0 + c < cols)
+                Y[j0 + c + v * ldy] = narrow<T>(r);
+        }
+        __syncthreads();
     }
 }
 

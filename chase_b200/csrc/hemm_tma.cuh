@@ -49,15 +49,20 @@
 namespace cb2
 {
 
-template <bool CPLX>
+// NARROW selects the tile width: 0 = the default tile (128 columns real, 64 complex), 1 = half of it, 2 = a quarter
+// (real only).  The 8 consumer warps are re-arranged so that the warp tile stays 32 columns wide: 2 x 4 warps of 64 x 32
+// (real default), 4 x 2 of 32 x 32, 8 x 1 of 16 x 32.  The narrow tiles serve the ragged last columns of a panel
+// (hemm_tma_launch splits it off), where the default tile would leave whole warps idle.
+template <bool CPLX, int NARROW = 0>
 struct HemmCfg
 {
+    static_assert(NARROW >= 0 && NARROW <= (CPLX ? 1 : 2), "tile variant");
     static constexpr int ELEM = CPLX ? 16 : 8;
     static constexpr int EPB = 128 / ELEM; // elements per 128-byte row
     static constexpr int BM = 128;
-    static constexpr int BN = CPLX ? 64 : 128;
+    static constexpr int BN = (CPLX ? 64 : 128) >> NARROW;
     static constexpr int BK = EPB;
-    static constexpr int WM = CPLX ? 32 : 64;
+    static constexpr int WM = (CPLX ? 32 : 64) >> NARROW;
     static constexpr int WN = 32;
     static constexpr int WARPS_M = BM / WM;
     static constexpr int KSTEPS = BK / 4;
@@ -211,15 +216,15 @@ struct HemmWalk
     }
 };
 
-template <class T, bool TA>
-__global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx>::THREADS, 1)
+template <class T, bool TA, int NARROW = 0>
+__global__ void __launch_bounds__(HemmCfg<Traits<T>::cplx, NARROW>::THREADS, 1)
     hemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const HemmParams<T> p)
 {
     using TR = Traits<T>;
     using C_ = typename TR::comp;
     constexpr bool CPLX = TR::cplx;
-    using CF = HemmCfg<CPLX>;
+    using CF = HemmCfg<CPLX, NARROW>;
     constexpr int BM = CF::BM, BN = CF::BN, BK = CF::BK, WM = CF::WM, WN = CF::WN, EPB = CF::EPB, ELEM = CF::ELEM;
     constexpr int MI = WM / 8, NJ = WN / 8, STAGES = CF::STAGES, KSTEPS = CF::KSTEPS;
     constexpr int IMUL = CPLX ? 2 : 1; // the tensor maps see complex<double> as two FLOAT64
@@ -685,13 +690,13 @@ inline void hemm_schedule(long long ntiles, long long nkt, int sms, bool ta, int
     }
 }
 
-template <class T>
-inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Traits<T>::comp alpha, const T* A,
-                           int64_t lda, const T* B, int64_t ldb, typename Traits<T>::comp beta, T* C, int64_t ldc,
-                           double shift, const double* theta, cudaStream_t st)
+template <class T, int NARROW>
+inline int hemm_tma_launch_cfg(bool ta, int64_t M, int64_t K, int64_t k, typename Traits<T>::comp alpha, const T* A,
+                               int64_t lda, const T* B, int64_t ldb, typename Traits<T>::comp beta, T* C, int64_t ldc,
+                               double shift, const double* theta, cudaStream_t st)
 {
     constexpr bool CPLX = Traits<T>::cplx;
-    using CF = HemmCfg<CPLX>;
+    using CF = HemmCfg<CPLX, NARROW>;
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc)
         return -4;
@@ -756,18 +761,63 @@ inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Tr
     p.epoch = ++sc->epoch;
     if (ta)
     {
-        CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T, true, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          CF::SMEM_BYTES));
-        hemm_tma_kernel<T, true><<<grid, CF::THREADS, CF::SMEM_BYTES, kcount(st)>>>(mapA, mapB, p);
+        hemm_tma_kernel<T, true, NARROW><<<grid, CF::THREADS, CF::SMEM_BYTES, kcount(st)>>>(mapA, mapB, p);
     }
     else
     {
-        CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CB2_CUDA_OK(cudaFuncSetAttribute(hemm_tma_kernel<T, false, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          CF::SMEM_BYTES));
-        hemm_tma_kernel<T, false><<<grid, CF::THREADS, CF::SMEM_BYTES, kcount(st)>>>(mapA, mapB, p);
+        hemm_tma_kernel<T, false, NARROW><<<grid, CF::THREADS, CF::SMEM_BYTES, kcount(st)>>>(mapA, mapB, p);
     }
     CB2_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// CHASE_B200_HEMM_SPLIT=0: one launch with the default tile for the whole panel (diagnostics); read at every launch
+inline bool hemm_split_enabled()
+{
+    const char* e = getenv("CHASE_B200_HEMM_SPLIT");
+    return e ? atoi(e) != 0 : true;
+}
+
+// The panel is cut into the columns that fill whole default tiles and the ragged rest.  Inside one launch every tile
+// costs the same, so the stream-K / hybrid schedule balances exactly; the rest runs as a second launch on the
+// narrowest tile that covers it (all 8 warps busy).  In a single launch the ragged tiles were booked as full tiles:
+// k = 1342 took as long as k = 1408 and k = 419 ran at 29 TFLOP/s where cuBLAS reaches 33.
+template <class T>
+inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Traits<T>::comp alpha, const T* A,
+                           int64_t lda, const T* B, int64_t ldb, typename Traits<T>::comp beta, T* C, int64_t ldc,
+                           double shift, const double* theta, cudaStream_t st)
+{
+    constexpr bool CPLX = Traits<T>::cplx;
+    constexpr int BN = HemmCfg<CPLX>::BN;
+    const int64_t k_full = (k / BN) * BN, k_rag = k - k_full;
+    if (!hemm_split_enabled() || k_rag == 0 || k_rag > (3 * BN) / 4)
+        return hemm_tma_launch_cfg<T, 0>(ta, M, K, k, alpha, A, lda, B, ldb, beta, C, ldc, shift, theta, st);
+    if (k_full > 0)
+    {
+        const int rc = hemm_tma_launch_cfg<T, 0>(ta, M, K, k_full, alpha, A, lda, B, ldb, beta, C, ldc, shift, theta, st);
+        if (rc)
+            return rc;
+    }
+    const T* Br = B + k_full * ldb;
+    T* Cr = C + k_full * ldc;
+    const double* th = theta ? theta + k_full : nullptr;
+    if constexpr (!CPLX)
+    {
+        if (k_rag <= BN / 4)
+            return hemm_tma_launch_cfg<T, 2>(ta, M, K, k_rag, alpha, A, lda, Br, ldb, beta, Cr, ldc, shift, th, st);
+        if (k_rag <= BN / 2)
+            return hemm_tma_launch_cfg<T, 1>(ta, M, K, k_rag, alpha, A, lda, Br, ldb, beta, Cr, ldc, shift, th, st);
+    }
+    else
+    {
+        if (k_rag <= BN / 2)
+            return hemm_tma_launch_cfg<T, 1>(ta, M, K, k_rag, alpha, A, lda, Br, ldb, beta, Cr, ldc, shift, th, st);
+    }
+    return hemm_tma_launch_cfg<T, 0>(ta, M, K, k_rag, alpha, A, lda, Br, ldb, beta, Cr, ldc, shift, th, st);
 }
 
 } // namespace cb2

@@ -675,16 +675,10 @@ int gemv_impl(int64_t rows, int64_t cols, const void* A, int64_t lda, const void
     cudaStream_t st = S(stream);
     if (rows <= 0 || cols <= 0 || nv <= 0)
         return 0;
-    // one warp per GEMV_CJ columns, 8 warps per block.  All blocks are resident at once (2 per SM at 128 registers);
-    // the group count per warp is made equal so that no warp walks one column group more than the others
-    int blocks;
-    {
-        const int64_t ngroups = (cols + GEMV_CJ - 1) / GEMV_CJ;
-        const int64_t max_warps = 148 * 2 * 8;
-        const int64_t per_warp = (ngroups + max_warps - 1) / max_warps;
-        const int64_t warps = (ngroups + per_warp - 1) / per_warp;
-        blocks = (int)std::max<int64_t>((warps + 7) / 8, 1);
-    }
+    // one warp per GEMV_CJ columns, 8 warps per block (scalar-load kernel)
+    const int blocks = (int)std::min<int64_t>((cols + 8 * GEMV_CJ - 1) / (8 * GEMV_CJ), 148 * 8);
+    // CTA-per-column-group kernel: persistent grid, 2 CTAs per SM
+    const int blk_blocks = (int)std::min<int64_t>((cols + GEMV_CJ - 1) / GEMV_CJ, 148 * 2);
     // 16-byte loads when every column of A and X starts on a 16-byte boundary (CHASE_B200_GEMV_VEC=0: scalar loads)
     constexpr int64_t VEC = 16 / (int64_t)sizeof(T) > 0 ? 16 / (int64_t)sizeof(T) : 1;
     static const bool vec_on = []
@@ -692,7 +686,8 @@ int gemv_impl(int64_t rows, int64_t cols, const void* A, int64_t lda, const void
         const char* e = getenv("CHASE_B200_GEMV_VEC");
         return !(e && atoi(e) == 0);
     }();
-    const bool vec = vec_on && lda % VEC == 0 && ldx % VEC == 0 && (((uintptr_t)A | (uintptr_t)X) & 15) == 0;
+    // (complex<double> already moves 16 bytes per element and measured slower on the CTA-per-group kernel)
+    const bool vec = vec_on && sizeof(T) < 16 && lda % VEC == 0 && ldx % VEC == 0 && (((uintptr_t)A | (uintptr_t)X) & 15) == 0;
     int v = 0;
     while (v < nv)
     {
@@ -701,7 +696,7 @@ int gemv_impl(int64_t rows, int64_t cols, const void* A, int64_t lda, const void
         if (nv - v >= 4)
         {
             if (vec)
-                gemv_conjT_vec_kernel<T, 4><<<blocks, 256, 0, kcount(st)>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
+                gemv_conjT_blk_kernel<T, 4><<<blk_blocks, 256, 0, kcount(st)>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
             else
                 gemv_conjT_kernel<T, 4><<<blocks, 256, 0, kcount(st)>>>(rows, cols, (const T*)A, lda, x, ldx, y, ldy);
             v += 4;

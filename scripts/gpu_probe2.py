@@ -1,6 +1,6 @@
 """Round-2 GPU probe (run under gpurun): A/B of HEMM kernel variants against same-box cuBLAS.
 
-  * consumer loop: CHASE_B200_HEMM_PIPE=0 (blocking wait per k-block) vs 1 (cross-k-block prefetch, staggered waits)
+  * ragged last-column tiles: CHASE_B200_HEMM_SPLIT=0 (one launch, default tile) vs 1 (ragged columns in a second launch on a narrow tile)
   * filter widths of a C2 solve (k = 1400, 1342, 609, 419) and the complex C4-like width
   * distributed local blocks (M x K rectangular, op(A) = A and A^H) with the hybrid schedule on/off
   * Lanczos gemv_conjT: GB/s against MEASURED_PEAKS.json
@@ -35,8 +35,8 @@ what = sys.argv[1:] or ["square", "rect", "gemv"]
 
 if "square" in what:
     res = []
-    for t, n, kc in [("d", 20000, 1400), ("d", 20000, 1342), ("d", 20000, 609), ("d", 20000, 419), ("z", 12000, 1400),
-                     ("z", 12000, 419)]:
+    for t, n, kc in [("d", 20000, 1400), ("d", 20000, 1342), ("d", 20000, 1300), ("d", 20000, 609), ("d", 20000, 419),
+                     ("d", 20000, 200), ("z", 12000, 1400), ("z", 12000, 1342), ("z", 12000, 419)]:
         dt = torch.float64 if t == "d" else torch.complex128
         f = 1 if t == "d" else 4
         ld = (n + 15) // 16 * 16
@@ -45,11 +45,11 @@ if "square" in what:
         C = torch.randn((kc, ld), dtype=dt, device="cuda")
         flops = 2.0 * f * n * n * kc
         r = dict(type=t, n=n, k=kc)
-        for pipe in ("0", "1"):
-            os.environ["CHASE_B200_HEMM_PIPE"] = pipe
+        for alt in ("0", "1"):  # ragged columns: single launch vs split launch
+            os.environ["CHASE_B200_HEMM_SPLIT"] = alt
             tk = timeit(lambda: k.hemm(n, kc, 0.5, A, ld, B, ld, -0.25, C, ld, 1.0))
-            r[f"pipe{pipe}_ms"] = tk * 1e3
-            r[f"pipe{pipe}_tflops"] = flops / tk / 1e12
+            r[f"alt{alt}_ms"] = tk * 1e3
+            r[f"alt{alt}_tflops"] = flops / tk / 1e12
         Cb = torch.empty_like(C)
         tb = timeit(lambda: torch.matmul(B, A, out=Cb))
         r["cublas_ms"], r["cublas_tflops"] = tb * 1e3, flops / tb / 1e12
@@ -57,7 +57,7 @@ if "square" in what:
         res.append(r)
         del A, B, C, Cb
     out["hemm_square"] = res
-    os.environ.pop("CHASE_B200_HEMM_PIPE", None)
+    os.environ.pop("CHASE_B200_HEMM_SPLIT", None)
 
 if "rect" in what:
     # local blocks of C2 on 2x1 / 2x2 / 4x2 grids, and of C4 (z N=120000) on 4x2 scaled to fit quickly
