@@ -793,31 +793,36 @@ inline int hemm_tma_launch(bool ta, int64_t M, int64_t K, int64_t k, typename Tr
 {
     constexpr bool CPLX = Traits<T>::cplx;
     constexpr int BN = HemmCfg<CPLX>::BN;
-    const int64_t k_full = (k / BN) * BN, k_rag = k - k_full;
-    if (!hemm_split_enabled() || k_rag == 0 || k_rag > (3 * BN) / 4)
+    if (!hemm_split_enabled() || k % BN == 0 || k % BN > (3 * BN) / 4)
         return hemm_tma_launch_cfg<T, 0>(ta, M, K, k, alpha, A, lda, B, ldb, beta, C, ldc, shift, theta, st);
-    if (k_full > 0)
+    // greedy strips: whole default tiles, then a half-width strip, then the narrowest tile for what is left
+    int64_t c0 = 0;
+    auto strip = [&](auto narrow_tag, int64_t cols) -> int
     {
-        const int rc = hemm_tma_launch_cfg<T, 0>(ta, M, K, k_full, alpha, A, lda, B, ldb, beta, C, ldc, shift, theta, st);
-        if (rc)
-            return rc;
-    }
-    const T* Br = B + k_full * ldb;
-    T* Cr = C + k_full * ldc;
-    const double* th = theta ? theta + k_full : nullptr;
+        constexpr int NARROW = decltype(narrow_tag)::value;
+        const int rc = hemm_tma_launch_cfg<T, NARROW>(ta, M, K, cols, alpha, A, lda, B + c0 * ldb, ldb, beta, C + c0 * ldc,
+                                                      ldc, shift, theta ? theta + c0 : nullptr, st);
+        c0 += cols;
+        return rc;
+    };
+    int rc = 0;
+    if (k >= BN)
+        rc = strip(std::integral_constant<int, 0>{}, (k / BN) * BN);
     if constexpr (!CPLX)
     {
-        if (k_rag <= BN / 4)
-            return hemm_tma_launch_cfg<T, 2>(ta, M, K, k_rag, alpha, A, lda, Br, ldb, beta, Cr, ldc, shift, th, st);
-        if (k_rag <= BN / 2)
-            return hemm_tma_launch_cfg<T, 1>(ta, M, K, k_rag, alpha, A, lda, Br, ldb, beta, Cr, ldc, shift, th, st);
+        if (!rc && k - c0 >= BN / 2)
+            rc = strip(std::integral_constant<int, 1>{}, BN / 2);
+        if (!rc && k - c0 > BN / 4)
+            rc = strip(std::integral_constant<int, 1>{}, k - c0);
+        else if (!rc && k - c0 > 0)
+            rc = strip(std::integral_constant<int, 2>{}, k - c0);
     }
     else
     {
-        if (k_rag <= BN / 2)
-            return hemm_tma_launch_cfg<T, 1>(ta, M, K, k_rag, alpha, A, lda, Br, ldb, beta, Cr, ldc, shift, th, st);
+        if (!rc && k - c0 > 0)
+            rc = strip(std::integral_constant<int, 1>{}, k - c0); // one or two 32-column tiles per row block
     }
-    return hemm_tma_launch_cfg<T, 0>(ta, M, K, k_rag, alpha, A, lda, Br, ldb, beta, Cr, ldc, shift, th, st);
+    return rc;
 }
 
 } // namespace cb2

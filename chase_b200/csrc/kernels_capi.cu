@@ -558,9 +558,12 @@ int heev_osj_impl(int64_t n64, const void* Gv, int64_t ldg, void* Zv, int64_t ld
     size_t smem;
     if (use_dmma)
     {
-        // 16 columns of cs elements + the per-warp partial Gram blocks in <= 216 KB (+ 10 KB static); cs = rpc + 4 gives the
-        // conflict-free stride (32 / 64 bytes mod 128)
-        const int cs_max = (int)((216 * 1024 / sizeof(C_) - OsjDmma<C_>::NRED) / OSJ_K);
+        // 16 columns of cs elements + the per-warp partial Gram blocks in what the kernel's static shared memory leaves
+        // of the 227 KB a CTA may use; cs = rpc + 4 gives the conflict-free stride (32 / 64 bytes mod 128)
+        cudaFuncAttributes fa;
+        CB2_CUDA_OK(cudaFuncGetAttributes(&fa, osj_round_dmma_kernel<C_>));
+        const size_t dyn_max = (size_t)227 * 1024 - fa.sharedSizeBytes - 256;
+        const int cs_max = (int)((dyn_max / sizeof(C_) - OsjDmma<C_>::NRED) / OSJ_K);
         const int rmax = (cs_max - 4) / 32 * 32;
         rpc = std::min((ldb + 31) / 32 * 32, rmax);
         cs = rpc + 4;

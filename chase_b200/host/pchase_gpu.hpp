@@ -587,9 +587,14 @@ public:
         return std::sqrt(nr[0]) <= tol * std::sqrt(nr[1]);
     }
     bool isPseudoHerm() override { return kPseudo; }
+    // The reference completes a distributed matrix from one triangle with ScaLAPACK's p?tranc and throws in builds
+    // without ScaLAPACK (linalg/internal/nccl/symOrHerm.hpp:96-158, 262-264).  This library is the ScaLAPACK-less
+    // configuration (chase_has_scalapack_ reports 0), so it mirrors that error; single-GPU matrices are completed
+    // (ChASEGPU::symOrHermMatrix).
     void symOrHermMatrix(char) override
     {
-        throw std::runtime_error("chase_b200: symOrHermMatrix is not available for distributed matrices yet");
+        throw std::runtime_error("For ChASE-MPI, symOrHermMatrix requires ScaLAPACK, which is not detected "
+                                 "(chase_b200 is built without ScaLAPACK: pass the full distributed matrix)");
     }
 
     void End() override
