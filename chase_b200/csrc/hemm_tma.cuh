@@ -640,14 +640,15 @@ inline bool hemm_remap_disabled()
     const char* e = getenv("CHASE_B200_HEMM_REMAP");
     return e && atoi(e) == 0;
 }
-// Hybrid schedule: stream-K only for the ragged end, k-aligned whole-tile waves before it.  Default: on for
-// op(A) = A (measured at N=20000, k=1400: DRAM reads 8.4 GB instead of 42 GB at the same 31.4 ms; complex N=12000:
-// 45.9 vs 45.6 ms), off for op(A) = A^H until that variant has been measured too.  CHASE_B200_HEMM_HYBRID=0/1
+// Hybrid schedule: stream-K only for the ragged end, k-aligned whole-tile waves before it.  Default: on for both operand
+// orientations.  Measured DRAM reads per launch at unchanged time (ncu, profiles/r2_hemm_rect_traffic.csv): op(A) = A,
+// N=20000, k=1400: 8.4 GB instead of 42 GB; local block 10000 x 20000 of the 2-GPU grid: op(A) = A 7.9 instead of 30.3 GB,
+// op(A) = A^H 3.7 instead of 15.3 GB; 10000 x 10000 (4 GPUs): 3.3 instead of 12.6-12.8 GB.  CHASE_B200_HEMM_HYBRID=0/1
 // forces it either way.
-inline bool hemm_hybrid_enabled(bool ta)
+inline bool hemm_hybrid_enabled(bool /*ta*/)
 {
     const char* e = getenv("CHASE_B200_HEMM_HYBRID");
-    return e ? atoi(e) != 0 : !ta;
+    return e ? atoi(e) != 0 : true;
 }
 inline bool hemm_streamk_disabled()
 {

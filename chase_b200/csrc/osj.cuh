@@ -461,8 +461,9 @@ __global__ void __launch_bounds__(OSJ_THREADS) osj_round_dmma_kernel(int n, int 
     extern __shared__ __align__(128) unsigned char osj_smem[];
     C* sB = reinterpret_cast<C*>(osj_smem);          // [K][cs]
     C* sRed = sB + (size_t)K * cs;                     // [8 warps][3 blocks][64]
-    __shared__ C sMb[2][K][K + 1];
-    __shared__ C sJb[2][K][K];
+    __shared__ C sM[K][K + 1];
+    __shared__ C sJ[K][K];
+    __shared__ JRot sR[K / 2];
     __shared__ int s_active;
     __shared__ int s_col[K];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -580,20 +581,20 @@ __global__ void __launch_bounds__(OSJ_THREADS) osj_round_dmma_kernel(int n, int 
             for (int w = 1; w < 8; ++w)
                 v = cadd(v, sRed[(w * 3 + b) * 64 + e]);
             if (b == 0)
-                sMb[0][i][j] = v;
+                sM[i][j] = v;
             else if (b == 2)
-                sMb[0][8 + i][8 + j] = v;
+                sM[8 + i][8 + j] = v;
             else
             {
-                sMb[0][i][8 + j] = v;
-                sMb[0][8 + j][i] = cconj(v);
+                sM[i][8 + j] = v;
+                sM[8 + j][i] = cconj(v);
             }
         }
     }
     // J = I
     {
         const int i = tid / K, j = tid % K;
-        sJb[0][i][j] = (i == j) ? from_real<C>(1.0) : czero<C>();
+        sJ[i][j] = (i == j) ? from_real<C>(1.0) : czero<C>();
     }
     __syncthreads();
 
@@ -602,8 +603,8 @@ __global__ void __launch_bounds__(OSJ_THREADS) osj_round_dmma_kernel(int n, int 
         const int i = tid / K, j = tid % K;
         if (i < j)
         {
-            const double a = creal(sMb[0][i][i]), b = creal(sMb[0][j][j]);
-            const double gg = sqrt(cabs2(sMb[0][i][j]));
+            const double a = creal(sM[i][i]), b = creal(sM[j][j]);
+            const double gg = sqrt(cabs2(sM[i][j]));
             if (a > 0.0 && b > 0.0)
             {
                 const double ratio = gg / sqrt(a * b);
@@ -622,23 +623,26 @@ __global__ void __launch_bounds__(OSJ_THREADS) osj_round_dmma_kernel(int n, int 
         atomicAdd(nrot, 1);
 
     // ---- phase 2: one cyclic sweep on M in shared memory (15 steps of 8 disjoint pairs), J accumulated ----
-    // One barrier per step: M and J are double-buffered and every thread recomputes the one or two rotations it
-    // applies from the current M (redundant arithmetic, but the 15 steps are a pure latency chain: with a separate
-    // "8 threads compute the rotations" stage the CTA spent 37 % of a round waiting on two barriers per step).
-    int cur = 0;
-    auto rot_of = [&](int pr, int p, int q) -> JRot
-    {
-        const double a = creal(sMb[pr][p][p]), b = creal(sMb[pr][q][q]);
-        const C gpq = sMb[pr][p][q];
-        // |g| > tol sqrt(a b)  <=>  |g|^2 > tol^2 a b  (no square root on the critical path)
-        const bool act = (a > 0.0 && b > 0.0) && (cabs2(gpq) > tol * tol * a * b);
-        return make_rot<C>(a, b, gpq, act ? 0.0 : 1e300);
-    };
     for (int step = 0; step < K - 1; ++step)
     {
+        if (tid < K / 2)
+        {
+            int p, q;
+            rr_pair(step, tid, K, p, q);
+            if (p > q)
+            {
+                const int t = p;
+                p = q;
+                q = t;
+            }
+            const double a = creal(sM[p][p]), b = creal(sM[q][q]);
+            const C gpq = sM[p][q];
+            const double thresh = (a > 0.0 && b > 0.0) ? tol * sqrt(a * b) : 1e300;
+            sR[tid] = make_rot<C>(a, b, gpq, thresh);
+        }
+        __syncthreads();
         if (tid < (K / 2) * (K / 2))
         {
-            // 2x2 block (pair ia rows, pair ib columns) of M <- Ja^H M Jb
             const int ia = tid / (K / 2), ib = tid % (K / 2);
             int pa, qa, pb, qb;
             rr_pair(step, ia, K, pa, qa);
@@ -655,11 +659,10 @@ __global__ void __launch_bounds__(OSJ_THREADS) osj_round_dmma_kernel(int n, int 
                 pb = qb;
                 qb = t;
             }
-            const JRot Ra = rot_of(cur, pa, qa);
-            const JRot Rb = (ia == ib) ? Ra : rot_of(cur, pb, qb);
-            C b00 = sMb[cur][pa][pb], b01 = sMb[cur][pa][qb], b10 = sMb[cur][qa][pb], b11 = sMb[cur][qa][qb];
+            const JRot Ra = sR[ia], Rb = sR[ib];
             if (Ra.active || Rb.active)
             {
+                C b00 = sM[pa][pb], b01 = sM[pa][qb], b10 = sM[qa][pb], b11 = sM[qa][qb];
                 rot_block<C>(b00, b01, b10, b11, Ra, Rb);
                 if (ia == ib)
                 {
@@ -668,15 +671,14 @@ __global__ void __launch_bounds__(OSJ_THREADS) osj_round_dmma_kernel(int n, int 
                     b01 = czero<C>();
                     b10 = czero<C>();
                 }
+                sM[pa][pb] = b00;
+                sM[pa][qb] = b01;
+                sM[qa][pb] = b10;
+                sM[qa][qb] = b11;
             }
-            sMb[cur ^ 1][pa][pb] = b00;
-            sMb[cur ^ 1][pa][qb] = b01;
-            sMb[cur ^ 1][qa][pb] = b10;
-            sMb[cur ^ 1][qa][qb] = b11;
         }
         else if (tid >= 128 && tid < 128 + K * (K / 2))
         {
-            // J <- J Jb : row i, pair ib
             const int t = tid - 128;
             const int i = t / (K / 2), ib = t % (K / 2);
             int pb, qb;
@@ -687,24 +689,17 @@ __global__ void __launch_bounds__(OSJ_THREADS) osj_round_dmma_kernel(int n, int 
                 pb = qb;
                 qb = tt;
             }
-            const JRot Rb = rot_of(cur, pb, qb);
-            C x = sJb[cur][i][pb], y = sJb[cur][i][qb];
+            const JRot Rb = sR[ib];
             if (Rb.active)
             {
                 const C ub = cconj(load_u<C>(Rb));
-                const C nx = csub(cmul(Rb.c, x), cmul(Rb.s, cmul(ub, y)));
-                const C ny = cadd(cmul(Rb.s, x), cmul(Rb.c, cmul(ub, y)));
-                x = nx;
-                y = ny;
+                const C x = sJ[i][pb], y = sJ[i][qb];
+                sJ[i][pb] = csub(cmul(Rb.c, x), cmul(Rb.s, cmul(ub, y)));
+                sJ[i][qb] = cadd(cmul(Rb.s, x), cmul(Rb.c, cmul(ub, y)));
             }
-            sJb[cur ^ 1][i][pb] = x;
-            sJb[cur ^ 1][i][qb] = y;
         }
         __syncthreads();
-        cur ^= 1;
     }
-    // K - 1 = 15 steps: the result sits in buffer 1
-    C(*sJ)[K] = sJb[cur];
 
     // ---- phase 3: Bp <- Bp J on DMMA; warp w owns the 8-row blocks w, w + 8, ... ---------------------------------
     C jf[4][2]; // J fragments: B operand of (k-step a, column block jb): J[4a + lq][8jb + lc]
