@@ -84,6 +84,35 @@ def local_block(N, gr, gc, cplx, device, transposed=False, lam=None):
     return A, lam
 
 
+def fill_local_block(ptr, ld, N, gr, gc, cplx, device, lam=None, chunk=4096):
+    """Writes this rank's block A[gr, gc] straight into the column-major device buffer at `ptr` (leading dimension `ld`
+    elements), `chunk` columns at a time: the same matrix as local_block(), without ever holding a second copy."""
+    import torch
+
+    lam, X, Y, coef = lowrank_terms(N, cplx, lam)
+    dt = torch.complex128 if cplx else torch.float64
+
+    class _View:  # zero-copy torch view of the solver's buffer: (n_loc, ld) row-major == column-major m_loc x n_loc
+        __cuda_array_interface__ = {"shape": (len(gc), int(ld)), "typestr": "<c16" if cplx else "<f8",
+                                    "data": (int(ptr), False), "version": 3}
+
+    H = torch.as_tensor(_View(), device=device)
+    Xl = torch.from_numpy(X[gr, :] * coef[None, :]).to(device).to(dt)  # m_loc x 9
+    Yl = torch.from_numpy(Y[gc, :]).to(device).to(dt)  # n_loc x 9
+    pos = {int(g): k for k, g in enumerate(gr)}
+    for c0 in range(0, len(gc), chunk):
+        c1 = min(c0 + chunk, len(gc))
+        blk = Yl[c0:c1].conj() @ Xl.T  # (c1 - c0) x m_loc: columns c0..c1 of the block, transposed
+        cols = [c for c in range(c0, c1) if int(gc[c]) in pos]
+        if cols:
+            rows = [pos[int(gc[c])] for c in cols]
+            blk[[c - c0 for c in cols], rows] += torch.from_numpy(lam[gc[cols]]).to(device).to(dt)
+        H[c0:c1, :len(gr)] = blk
+        del blk
+    torch.cuda.synchronize()
+    return lam
+
+
 def _flag(L, name, v):
     getattr(L, name)(ctypes.byref(ctypes.c_int(v)))
 

@@ -177,6 +177,22 @@ class PChASE:
         if rc != 0:
             raise RuntimeError("chase_b200: device matrix hand-over failed")
 
+    def device_matrix(self):
+        """(device pointer, leading dimension) of the solver's own column-major local block, for callers that generate
+        the block in place (it then exists only once in HBM); call mark_device_matrix() when it is filled."""
+        ptr, ld = ctypes.c_void_p(), ctypes.c_longlong()
+        rc = self._lib.chase_b200_dist_device_matrix_(ctypes.c_char_p(self.pfx.encode()), ctypes.byref(ptr), ctypes.byref(ld))
+        if rc != 0:
+            raise RuntimeError("chase_b200: no active distributed solver")
+        return ptr.value, ld.value
+
+    def mark_device_matrix(self):
+        import torch
+
+        torch.cuda.synchronize()
+        if self._lib.chase_b200_dist_mark_device_matrix_(ctypes.c_char_p(self.pfx.encode())) != 0:
+            raise RuntimeError("chase_b200: no active distributed solver")
+
     def row_indices(self):
         return global_indices(self.N, self.grid[0], self.mb, self.i)
 

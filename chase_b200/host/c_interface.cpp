@@ -749,6 +749,47 @@ extern "C"
     // Device-resident input for matrices that should never exist on the host (C4: 28.8 GB per GPU): copies a
     // column-major device block (m_loc x n_loc, leading dimension ld_src) into the active distributed solver and marks
     // it resident, so that p?chase_ does not read the host pointer given at init.
+    // In-place variant of the hand-over below for blocks that only fit once (BASELINE config C4 on 2 GPUs: 115 GB per
+    // GPU): returns the solver's own device buffer (column-major local block, leading dimension *ld_out) so that the
+    // caller generates the block directly into it, then chase_b200_dist_mark_device_matrix_ declares it valid.
+    int chase_b200_dist_device_matrix_(char* type, void** ptr_out, long long* ld_out)
+    {
+        auto get = [&](auto& inst) -> int
+        {
+            if (!inst.solver)
+                return -1;
+            *ptr_out = (void*)inst.solver->device_H();
+            *ld_out = (long long)inst.solver->device_lda();
+            return 0;
+        };
+        switch (*type)
+        {
+            case 'd': return get(PD::get());
+            case 's': return get(PS::get());
+            case 'z': return PZP::get().solver ? get(PZP::get()) : get(PZ::get());
+            case 'c': return PCP::get().solver ? get(PCP::get()) : get(PC::get());
+        }
+        return -1;
+    }
+    int chase_b200_dist_mark_device_matrix_(char* type)
+    {
+        auto mark = [&](auto& inst) -> int
+        {
+            if (!inst.solver)
+                return -1;
+            inst.solver->mark_matrix_on_device();
+            g_matrix_resident = 1;
+            return 0;
+        };
+        switch (*type)
+        {
+            case 'd': return mark(PD::get());
+            case 's': return mark(PS::get());
+            case 'z': return PZP::get().solver ? mark(PZP::get()) : mark(PZ::get());
+            case 'c': return PCP::get().solver ? mark(PCP::get()) : mark(PC::get());
+        }
+        return -1;
+    }
     int chase_b200_dist_load_device_matrix_(char* type, const void* src_dev, long long* ld_src)
     {
         auto load = [&](auto& inst) -> int

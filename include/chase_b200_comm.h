@@ -49,6 +49,10 @@ extern "C"
        read the host matrix pointer (which may then be NULL at init).  For matrices that must never exist on the host
        (BASELINE config C4: 28.8 GB per GPU). */
     int chase_b200_dist_load_device_matrix_(char* type, const void* src_dev, long long* ld_src);
+    /* In-place variant for blocks that fit only once in HBM: the solver's own device buffer of the local block
+       (column-major, leading dimension *ld_out elements) to be filled by the caller, then declared valid. */
+    int chase_b200_dist_device_matrix_(char* type, void** ptr_out, long long* ld_out);
+    int chase_b200_dist_mark_device_matrix_(char* type);
     /* Fortran callers hold the communicator as an INTEGER (the reference's MPI_Fint arguments of the `_f_` entry points,
        chase_c_interface.cpp:2425-2900): chase_b200_comm_c2f registers the handle and returns its index (>= 1),
        chase_b200_comm_f2c maps it back (NULL if unknown).  Counterparts of MPI_Comm_c2f / MPI_Comm_f2c. */

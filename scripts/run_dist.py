@@ -49,6 +49,8 @@ ap.add_argument("--lam-max", type=float, default=100.0, help="--pseudo: positive
 ap.add_argument("--upperb-scale", type=float, default=1.0,
                 help="chase_set_upperb_scale_rate_: safety factor on the Lanczos estimate of max(lambda^2)")
 ap.add_argument("--max-iter", type=int, default=25)
+ap.add_argument("--in-place", action="store_true",
+                help="generate the local block directly into the solver's device buffer (no second copy)")
 a = ap.parse_args()
 
 L = chase_b200.lib()
@@ -64,13 +66,20 @@ dt = {"z": np.complex128, "c": np.complex64, "d": np.float64}[a.type]
 tol = a.tol or (1e-10 if a.type in ("z", "d") else 1e-5)
 solver = cd.PChASE(world, a.N, a.nev, a.nex, dt, grid=(r, c), major="R", mb=a.nb, nb=a.nb, pseudo=a.pseudo)
 # row-major (n_loc, m_loc) == column-major m_loc x n_loc with ld = m_loc
-if a.pseudo:
+if a.in_place and not a.pseudo:
+    # the block is generated straight into the solver's buffer (it exists once in HBM): C4 on 2 GPUs = 115 GB per GPU
+    ptr, ld = solver.device_matrix()
+    lam = bd.fill_local_block(ptr, ld, a.N, gr, gc, cplx, f"cuda:{world.device}")
+    solver.mark_device_matrix()
+    At = None
+elif a.pseudo:
     At, lam = bd.bse_local_block(a.N, gr, gc, f"cuda:{world.device}",
                                  dtype=torch.complex128 if a.type == "z" else torch.complex64, transposed=True,
                                  lam_max=a.lam_max)
 else:
     At, lam = bd.local_block(a.N, gr, gc, cplx, f"cuda:{world.device}", transposed=True)
-solver.load_device_matrix(At.data_ptr(), len(gr))
+if At is not None:
+    solver.load_device_matrix(At.data_ptr(), len(gr))
 del At
 torch.cuda.empty_cache()
 if a.seq > 1 and a.pseudo:
