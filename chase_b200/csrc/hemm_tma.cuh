@@ -43,6 +43,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <type_traits>
 #include <utility>
 
@@ -617,13 +618,24 @@ struct HemmScratch
     unsigned* flags = nullptr;
     unsigned epoch = 0;
 };
-inline HemmScratch* hemm_scratch(int dev, cudaStream_t st, int sms)
+inline std::mutex& hemm_scratch_mutex()
+{
+    static std::mutex m;
+    return m;
+}
+inline std::map<std::pair<int, cudaStream_t>, HemmScratch>& hemm_scratch_pool()
 {
     static std::map<std::pair<int, cudaStream_t>, HemmScratch> pool;
+    return pool;
+}
+inline HemmScratch* hemm_scratch(int dev, cudaStream_t st, int sms)
+{
+    std::lock_guard<std::mutex> lk(hemm_scratch_mutex());
+    auto& pool = hemm_scratch_pool();
     auto key = std::make_pair(dev, st);
     auto it = pool.find(key);
     if (it != pool.end())
-        return &it->second;
+        return &it->second; // std::map nodes are stable: the pointer stays valid while other streams are added
     HemmScratch sc;
     const size_t slot_doubles = (size_t)HemmCfg<false>::BM * HemmCfg<false>::BN; // == complex BM*BN*2
     if (cudaMalloc(&sc.slots, (size_t)sms * slot_doubles * sizeof(double)) != cudaSuccess)
@@ -633,6 +645,24 @@ inline HemmScratch* hemm_scratch(int dev, cudaStream_t st, int sms)
     if (cudaMemset(sc.flags, 0, (size_t)sms * sizeof(unsigned)) != cudaSuccess)
         return nullptr;
     return &(pool[key] = sc);
+}
+// called by the owner of a stream before it destroys it: frees the stream's slots (a later stream whose handle value
+// happens to be re-used must not inherit them)
+inline void hemm_scratch_release(cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(hemm_scratch_mutex());
+    auto& pool = hemm_scratch_pool();
+    for (auto it = pool.begin(); it != pool.end();)
+    {
+        if (it->first.second == st)
+        {
+            cudaFree(it->second.slots);
+            cudaFree(it->second.flags);
+            it = pool.erase(it);
+        }
+        else
+            ++it;
+    }
 }
 // CHASE_B200_HEMM_REMAP=0 walks the plain raster (diagnostics); read at every launch
 inline bool hemm_remap_disabled()

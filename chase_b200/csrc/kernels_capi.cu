@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <numeric>
 #include <vector>
 
@@ -64,6 +65,21 @@ inline std::map<const void*, WideCopy>& wide_registry()
 {
     static std::map<const void*, WideCopy> r;
     return r;
+}
+inline std::mutex& wide_mutex()
+{
+    static std::mutex m;
+    return m;
+}
+// copy of the entry under the lock (solvers on different host threads register / unregister concurrently)
+inline bool wide_lookup(const void* A, WideCopy* out)
+{
+    std::lock_guard<std::mutex> lk(wide_mutex());
+    auto it = wide_registry().find(A);
+    if (it == wide_registry().end())
+        return false;
+    *out = it->second;
+    return true;
 }
 template <class T>
 struct WideOf;
@@ -183,10 +199,9 @@ int hemm_rect_impl(int ta, int64_t M, int64_t K, int64_t k, double are, double a
             }
         }
         using TW = typename WideOf<T>::type;
-        auto it = wide_registry().find(A);
-        if (it != wide_registry().end() && K > 0)
+        WideCopy w;
+        if (K > 0 && wide_lookup(A, &w))
         {
-            const WideCopy& w = it->second;
             const int64_t ldbw = (K + 15) / 16 * 16, ldcw = (M + 15) / 16 * 16;
             TW* Bw = (TW*)w.scratch;
             TW* Cw = Bw + ldbw * k;
@@ -1017,21 +1032,26 @@ extern "C" int chase_b200_widen_register(const void* A, void* A_wide, int64_t ld
     w.cols = cols;
     w.scratch = scratch;
     w.scratch_bytes = scratch_bytes;
-    wide_registry()[A] = w;
+    {
+        std::lock_guard<std::mutex> lk(wide_mutex());
+        wide_registry()[A] = w;
+    }
     return 0;
 }
 extern "C" int chase_b200_widen_unregister(const void* A)
 {
-    wide_registry().erase(A);
+    {
+        std::lock_guard<std::mutex> lk(wide_mutex());
+        wide_registry().erase(A);
+    }
     return 0;
 }
 // refresh the FP64 copy after the narrow matrix changed (upload); type: 's' or 'c'
 extern "C" int chase_b200_widen_sync(char type, const void* A, void* stream)
 {
-    auto it = wide_registry().find(A);
-    if (it == wide_registry().end())
+    WideCopy w;
+    if (!wide_lookup(A, &w))
         return -2;
-    const WideCopy& w = it->second;
     if (w.rows <= 0 || w.cols <= 0)
         return 0;
     cudaStream_t st = S(stream);
@@ -1065,6 +1085,13 @@ extern "C" int chase_b200_convert(char from, char to, int64_t rows, int64_t cols
     else
         return -2;
     CB2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// frees the per-stream scratch of the filter HEMM; call before destroying a stream that ran it
+extern "C" int chase_b200_stream_release(void* stream)
+{
+    hemm_scratch_release(S(stream));
     return 0;
 }
 

@@ -154,7 +154,10 @@ public:
         for (void* p : allocs_)
             cudaFree(p);
         if (stream_)
+        {
+            chase_b200_stream_release(stream_);
             cudaStreamDestroy(stream_);
+        }
     }
 
     // ---- ChaseBase ----------------------------------------------------------

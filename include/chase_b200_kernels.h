@@ -202,6 +202,9 @@ extern "C"
        the copies behind the mixed-precision filter (reference linalg/internal/cuda/precision_conversion.cu:20-55). */
     int chase_b200_convert(char from, char to, int64_t rows, int64_t cols, const void* src, int64_t lds, void* dst,
                            int64_t ldd, void* stream);
+    /* The filter HEMM keeps stream-K hand-over slots per (device, stream); the owner of a stream releases them before
+       cudaStreamDestroy (a later stream with the same handle value must not inherit them). */
+    int chase_b200_stream_release(void* stream);
     size_t chase_b200_trsm_ws_bytes(int64_t n, int elem_bytes);
     size_t chase_b200_hhqr_ws_bytes(int64_t rows, int64_t n, int elem_bytes);
     size_t chase_b200_heev_ws_bytes(int64_t n, int is_complex);
