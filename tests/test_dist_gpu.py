@@ -38,3 +38,35 @@ def test_two_ranks():
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
 def test_four_ranks():
     _run(4)
+
+
+def test_local_block_generated_in_place_matches_the_copied_hand_over():
+    """chase_b200_dist_device_matrix_ / _mark_device_matrix_ (blocks that fit only once in HBM: C4 on 2 GPUs): filling
+    the solver's own buffer with bench_dist.fill_local_block gives the same solve as generating the block separately and
+    handing it over with chase_b200_dist_load_device_matrix_."""
+    import numpy as np
+
+    from chase_b200 import bench_dist as bd
+    from chase_b200 import dist as cd
+
+    world = cd.World(0, 1, 0)
+    N, nev, nex, nb = 1800, 60, 30, 64
+    gr, gc = cd.global_indices(N, 1, nb, 0), cd.global_indices(N, 1, nb, 0)
+    res = []
+    for in_place in (False, True):
+        s = cd.PChASE(world, N, nev, nex, np.complex128, grid=(1, 1), major="R", mb=nb, nb=nb)
+        if in_place:
+            ptr, ld = s.device_matrix()
+            lam = bd.fill_local_block(ptr, ld, N, gr, gc, True, "cuda:0", chunk=500)
+            s.mark_device_matrix()
+        else:
+            At, lam = bd.local_block(N, gr, gc, True, "cuda:0", transposed=True)
+            s.load_device_matrix(At.data_ptr(), len(gr))
+            del At
+        res.append(s.solve(copy=True))
+        s.finalize()
+    world.close()
+    a, b = res
+    assert a.iterations == b.iterations and a.filtered_vecs == b.filtered_vecs
+    assert np.max(np.abs(a.ritzv[:nev] - lam[:nev]) / lam[:nev]) < 1e-10
+    assert np.max(np.abs(a.ritzv[:nev] - b.ritzv[:nev])) < 1e-12
