@@ -76,6 +76,20 @@ extern "C" int chase_b200_tf32_sync(char type, const void* A, void* stream)
     CB2_CUDA_OK(cudaGetLastError());
     return 0;
 }
+// refresh the lo parts of `cnt` elements given by linear element indices (device array) after an in-place update
+extern "C" int chase_b200_tf32_sync_list(char type, const void* A, int64_t cnt, const int64_t* lin_dev, void* stream)
+{
+    Tf32Reg r;
+    if (!tf32_lookup(A, &r))
+        return -2;
+    if (cnt <= 0)
+        return 0;
+    const int fpe = (type == 'c' || type == 'C') ? 2 : 1;
+    const int blocks = (int)std::min<long long>((cnt + 255) / 256, 148 * 4);
+    tf32_split_lo_list_kernel<<<blocks, 256, 0, kcount(S(stream))>>>(cnt, (const long long*)lin_dev, fpe, (const float*)A, (float*)r.lo);
+    CB2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 extern "C" void chase_b200_tf32_set_terms(int terms) { g_terms = terms >= 4 ? 4 : 3; }
 extern "C" size_t chase_b200_hemm_tf32_scratch_bytes(int64_t K, int64_t k, int elem_bytes)
 {

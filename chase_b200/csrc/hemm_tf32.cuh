@@ -425,6 +425,17 @@ __global__ void __launch_bounds__(256) tf32_split_lo_kernel(long long n4, const 
     }
 }
 
+// lo parts of selected elements (linear element indices into the matrix): the distributed backend shifts the diagonal
+// entries of its local block in place (pChASEGPU::Shift) and refreshes their lo parts with this
+__global__ void __launch_bounds__(256) tf32_split_lo_list_kernel(long long cnt, const long long* __restrict__ lin,
+                                                                  int floats_per_elem, const float* __restrict__ src,
+                                                                  float* __restrict__ dst)
+{
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (long long)gridDim.x * blockDim.x)
+        for (int f = 0; f < floats_per_elem; ++f)
+            dst[lin[t] * floats_per_elem + f] = tf32_lo(src[lin[t] * floats_per_elem + f]);
+}
+
 // Panel views.  Real:    v0 = lo(s B)                                (hi = B itself; s B copied to v1 when sflip)
 //               Complex: v0 = lo(s B), v1 = [s bi, -s br], v2 = lo(v1), v3 = s B (only when sflip)
 // s = -1 on rows >= sflip (sflip > 0), else 1.

@@ -143,6 +143,19 @@ public:
             wide_scratch_ = alloc<unsigned char>(wide_scratch_bytes_);
             chase_b200_widen_register(dH_, dHw_, (int64_t)lda_, (int64_t)m_loc_, (int64_t)n_loc_, wide_scratch_,
                                       wide_scratch_bytes_);
+            // The V -> W half of every distributed product, A_loc^H V, is the native orientation of the tcgen05
+            // kind::tf32 kernel (hemm_tf32.cuh): with the lo part of the local block registered (kind 2 = only
+            // op(A) = A^H) it runs there at ~5x the DMMA rate; the W -> V half (A_loc W, M-major operand) stays on the
+            // FP64 copy.  CHASE_B200_FP32_PATH=fp64copy keeps both halves on the copy.
+            const char* pth = std::getenv("CHASE_B200_FP32_PATH");
+            if (!(pth && std::string(pth) != "tf32") && m_loc_ >= 128 && n_loc_ >= 128)
+            {
+                dHl_ = alloc<T>(lda_ * std::max<std::size_t>(n_loc_, 1));
+                tf32_scratch_bytes_ = chase_b200_hemm_tf32_scratch_bytes((int64_t)m_loc_, (int64_t)nc_, (int)sizeof(T));
+                tf32_scratch_ = alloc<unsigned char>(tf32_scratch_bytes_);
+                chase_b200_tf32_register(dH_, dHl_, (int64_t)lda_, (int64_t)m_loc_, (int64_t)n_loc_, 2, tf32_scratch_,
+                                         tf32_scratch_bytes_);
+            }
         }
     }
     pChASEGPU(const pChASEGPU&) = delete;
@@ -150,6 +163,8 @@ public:
     {
         if (dHw_)
             chase_b200_widen_unregister(dH_);
+        if (dHl_)
+            chase_b200_tf32_unregister(dH_);
         cudaStreamSynchronize(stream_);
         for (void* p : allocs_)
             cudaFree(p);
@@ -220,6 +235,8 @@ public:
         if (dHw_ && !wide_valid_)
         {
             CB2_KCHECK(chase_b200_widen_sync(kCplx ? 'c' : 's', dH_, stream_));
+            if (dHl_)
+                CB2_KCHECK(chase_b200_tf32_sync(kCplx ? 'c' : 's', dH_, stream_));
             wide_valid_ = true;
         }
         reset_perm();
@@ -236,6 +253,8 @@ public:
             using TW = typename std::conditional<kCplx, std::complex<double>, double>::type;
             CB2_KCHECK(b200::K<TW>::shift_diag_list((int64_t)ndiag_, diag_lin_, dHw_, (double)std::real(c), stream_));
         }
+        if (dHl_) // ... and the lo parts of the shifted entries
+            CB2_KCHECK(chase_b200_tf32_sync_list(kCplx ? 'c' : 's', dH_, (int64_t)ndiag_, diag_lin_, stream_));
         if (isunshift)
             next_ = NextOp::bAc;
     }
@@ -388,8 +407,10 @@ public:
         // replicas of V1 inside a grid row are re-synchronised first (pchase_gpu.hpp:1631-1633)
         if (grid_.c > 1)
             comm_.broadcast(Q, ldv_ * block, 0, comm_.row(), stream_);
-        // W1 = A^H Q (row layout)
+        // W1 = A^H Q (row layout); FP32 types: all four TF32 partial products for the projected matrix
+        chase_b200_tf32_set_terms(4);
         hemm_v2w(T(1), Q, T(0), W1, block);
+        chase_b200_tf32_set_terms(3);
         // W2 = Q in row layout
         redistribute_v2w(Q, W2, block);
         // G = W2^H W1 summed over the grid row, then made bit-identical everywhere
@@ -1239,6 +1260,9 @@ private:
     T* dW_[4] = {nullptr, nullptr, nullptr, nullptr};
     T *dM_ = nullptr, *dRinv_ = nullptr, *dT_ = nullptr, *dFull_ = nullptr; // pseudo-Hermitian only
     T* dPack_ = nullptr; // packed triangle of a Gram / projected matrix (allreduce payload)
+    T* dHl_ = nullptr;   // lo part of the TF32 split of an FP32 local block (A_loc^H V on the tcgen05 kernel)
+    unsigned char* tf32_scratch_ = nullptr;
+    std::size_t tf32_scratch_bytes_ = 0;
     unsigned char *dHw_ = nullptr, *wide_scratch_ = nullptr; // FP64 copy of an FP32 local block + panel scratch
     std::size_t wide_scratch_bytes_ = 0;
     bool wide_valid_ = false;

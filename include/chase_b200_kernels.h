@@ -197,6 +197,8 @@ extern "C"
                                  void* scratch, size_t scratch_bytes);
     int chase_b200_tf32_unregister(const void* A);
     int chase_b200_tf32_sync(char type, const void* A, void* stream);
+    /* same for `cnt` elements given by linear element indices (device array): after an in-place diagonal shift */
+    int chase_b200_tf32_sync_list(char type, const void* A, int64_t cnt, const int64_t* lin_dev, void* stream);
     void chase_b200_tf32_set_terms(int terms);
     /* Precision change of a rows x cols column-major array, (from, to) in {'d'->'s', 's'->'d', 'z'->'c', 'c'->'z'}:
        the copies behind the mixed-precision filter (reference linalg/internal/cuda/precision_conversion.cu:20-55). */

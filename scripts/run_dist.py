@@ -78,6 +78,8 @@ elif a.pseudo:
                                  lam_max=a.lam_max)
 else:
     At, lam = bd.local_block(a.N, gr, gc, cplx, f"cuda:{world.device}", transposed=True)
+    if a.type == "c":  # the generator works in double precision
+        At = At.to(torch.complex64)
 if At is not None:
     solver.load_device_matrix(At.data_ptr(), len(gr))
 del At
@@ -96,6 +98,8 @@ for s in range(a.solves * a.seq):
         # next problem of the sequence: same Q, perturbed spectrum; previous eigenpairs stay in solver.V / ritzv
         lam_s = bd.sequence_spectrum(a.N, step, a.perturb)
         At, lam = bd.local_block(a.N, gr, gc, cplx, f"cuda:{world.device}", transposed=True, lam=lam_s)
+        if a.type == "c":
+            At = At.to(torch.complex64)
         lam = np.sort(lam)
         solver.load_device_matrix(At.data_ptr(), len(gr))
         del At
