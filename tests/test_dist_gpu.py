@@ -49,23 +49,32 @@ def test_local_block_generated_in_place_matches_the_copied_hand_over():
     from chase_b200 import bench_dist as bd
     from chase_b200 import dist as cd
 
+    import ctypes
+
+    import chase_b200
+
     world = cd.World(0, 1, 0)
     N, nev, nex, nb = 1800, 60, 30, 64
     gr, gc = cd.global_indices(N, 1, nb, 0), cd.global_indices(N, 1, nb, 0)
     res = []
-    for in_place in (False, True):
-        s = cd.PChASE(world, N, nev, nex, np.complex128, grid=(1, 1), major="R", mb=nb, nb=nb)
-        if in_place:
-            ptr, ld = s.device_matrix()
-            lam = bd.fill_local_block(ptr, ld, N, gr, gc, True, "cuda:0", chunk=500)
-            s.mark_device_matrix()
-        else:
-            At, lam = bd.local_block(N, gr, gc, True, "cuda:0", transposed=True)
-            s.load_device_matrix(At.data_ptr(), len(gr))
-            del At
-        res.append(s.solve(copy=True))
-        s.finalize()
-    world.close()
+    try:
+        for in_place in (False, True):
+            s = cd.PChASE(world, N, nev, nex, np.complex128, grid=(1, 1), major="R", mb=nb, nb=nb)
+            if in_place:
+                ptr, ld = s.device_matrix()
+                lam = bd.fill_local_block(ptr, ld, N, gr, gc, True, "cuda:0", chunk=500)
+                s.mark_device_matrix()
+            else:
+                At, lam = bd.local_block(N, gr, gc, True, "cuda:0", transposed=True)
+                s.load_device_matrix(At.data_ptr(), len(gr))
+                del At
+            res.append(s.solve(copy=True))
+            s.finalize()
+    finally:
+        # the device hand-over switches the process-global "matrix resident" mode on: later solves in this process
+        # must read their host matrices again
+        chase_b200.lib().chase_b200_set_matrix_resident_(ctypes.byref(ctypes.c_int(0)))
+        world.close()
     a, b = res
     assert a.iterations == b.iterations and a.filtered_vecs == b.filtered_vecs
     assert np.max(np.abs(a.ritzv[:nev] - lam[:nev]) / lam[:nev]) < 1e-10
