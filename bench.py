@@ -420,6 +420,16 @@ def ours(a):
             line["cpu_baseline"] = {"value": r["tflops_per_solve"], "unit": "TFLOP/s", "cores": r["threads"],
                                     "kind": "reference", "sample": sample_text(r),
                                     "filter_phase_tflops": r["tflops_filter_phase"], "host_cores": os.cpu_count()}
+            try:  # the one full-size run of the same binary on this class of box (recorded, not re-run: 460 s)
+                fs = json.load(open(os.path.join(ROOT, "profiles", "r2_ref_cpu_c2_full.json")))
+                if a.workload == "c2":
+                    line["cpu_baseline"]["full_size_recorded"] = {
+                        "time_to_solution_s": fs["timings_s"]["All"], "filter_s": fs["timings_s"]["Filter"],
+                        "iterations": fs["iterations"], "filtered_vecs": fs["filtered_vecs"],
+                        "value": fs["tflops_per_time_to_solution"], "unit": "TFLOP/s", "cores": 16,
+                        "source": "profiles/r2_ref_cpu_c2_full.json"}
+            except Exception:  # noqa: BLE001
+                pass
     if not a.no_gpu_reference:
         g = run_reference_gpu(a.workload, a.gpu_ref_repeats)
         line["gpu_reference"] = g

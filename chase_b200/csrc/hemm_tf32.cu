@@ -18,7 +18,7 @@ std::map<const void*, Tf32Reg>& registry()
     static std::map<const void*, Tf32Reg> r;
     return r;
 }
-int g_terms = 3;
+thread_local int g_terms = 3; // per host thread: one host thread drives one solver instance
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 } // namespace
 
