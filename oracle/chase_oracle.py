@@ -1159,3 +1159,44 @@ def solve_problem_pseudo(H: np.ndarray, nev: int, nex: int, cfg: Config | None =
     be = OracleBackendPseudo(H, nev, nex)
     tr = solve_pseudo(be, cfg)
     return be.ritzv[:nev + nex].copy(), be.resid[:nev + nex].copy(), be.V1.copy(), tr, be
+
+
+# ---- TF32 operand splitting of the single-precision filter product (chase_b200/csrc/hemm_tf32.cuh) ---------------------
+# TEST INFRASTRUCTURE: a statement of the operand preparation of the tcgen05 kind::tf32 kernel that replaces the
+# cublasSgemm / cublasCgemm of the reference's ChASEGPU::HEMM (external/cublaspp/cublaspp.hpp:563, 623).  The tensor core
+# reads the upper 19 bits of an FP32 container (hi = truncation); the kernel keeps lo = rna_tf32(x - hi) beside it and
+# forms A B ~ A_hi B_hi + A_hi B_lo + A_lo B_hi (+ A_lo B_lo).
+def tf32_trunc(x: np.ndarray) -> np.ndarray:
+    """What kind::tf32 sees of an FP32 value: the low 13 mantissa bits dropped."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)
+    return b.view(np.float32)
+
+
+def tf32_rna(x: np.ndarray) -> np.ndarray:
+    """cvt.rna.tf32.f32: round to nearest, ties away from zero, to 10 explicit mantissa bits."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((b + np.uint64(0x1000)) & np.uint64(0xFFFFE000)).astype(np.uint32)
+    out = r.view(np.float32).copy()
+    bad = ~np.isfinite(np.asarray(x, dtype=np.float32))
+    out[bad] = np.asarray(x, dtype=np.float32)[bad]
+    return out
+
+
+def tf32_split(x: np.ndarray):
+    """(hi, lo) as the kernel uses them: hi = tf32_trunc(x) (implicit, the stored value itself), lo = rna(x - hi)."""
+    x = np.asarray(x, dtype=np.float32)
+    hi = tf32_trunc(x)
+    lo = tf32_rna((x - hi).astype(np.float32))
+    return hi, lo
+
+
+def gemm_tf32_split(A: np.ndarray, B: np.ndarray, terms: int = 3) -> np.ndarray:
+    """A @ B from the split operands, products accumulated exactly (float64): isolates the error of the 3- / 4-term
+    splitting from the accumulation error of the hardware."""
+    Ah, Al = tf32_split(A)
+    Bh, Bl = tf32_split(B)
+    f = np.float64
+    C = Ah.astype(f) @ Bh.astype(f) + Ah.astype(f) @ Bl.astype(f) + Al.astype(f) @ Bh.astype(f)
+    if terms >= 4:
+        C = C + Al.astype(f) @ Bl.astype(f)
+    return C

@@ -141,3 +141,31 @@ def test_host_tridiagonal_eigensolver_matches_lapack(n):
     if n > 1:
         wl, Zl = sla.eigh_tridiagonal(d, e[: n - 1])
         assert np.max(np.abs(np.abs(Z[0]) - np.abs(Zl[0]))) < 1e-9  # the DoS weights |z_0k|^2 agree
+
+
+def test_tf32_split_statement_of_the_fp32_filter_product():
+    """oracle.tf32_split / gemm_tf32_split (statement of the operand preparation of csrc/hemm_tf32.cuh): hi is a TF32
+    value, hi + lo reproduces x to 2^-21, one TF32 product is 1e-3 accurate, three partial products reach 2^-20 of the
+    dot-product scale (a bias: the dropped lo*lo term has the sign of the product) and four reach the FP32 level -- why the
+    filter uses 3 terms and the Rayleigh-Ritz / residual products 4."""
+    from oracle import chase_oracle as co
+
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal(100000) * np.exp(rng.uniform(-20, 20, 100000))).astype(np.float32)
+    hi, lo = co.tf32_split(x)
+    assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)
+    assert np.all(np.abs(hi) <= np.abs(x)) and np.all(np.sign(lo) * np.sign(x) >= 0)  # truncation: lo has x's sign
+    rel = np.abs((hi.astype(np.float64) + lo.astype(np.float64)) - x) / np.abs(x)
+    assert rel.max() <= 2.0 ** -21
+    M, K, N = 64, 4096, 48
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    scale = np.sqrt(K)  # RMS of an entry of the result
+    e1 = np.abs(co.tf32_trunc(A).astype(np.float64) @ co.tf32_trunc(B).astype(np.float64) - ref).max() / scale
+    e3 = np.abs(co.gemm_tf32_split(A, B, 3) - ref).max() / scale
+    e4 = np.abs(co.gemm_tf32_split(A, B, 4) - ref).max() / scale
+    e32 = np.abs((A @ B).astype(np.float64) - ref).max() / scale
+    assert 1e-4 < e1 < 1e-2  # plain TF32: not FP32-accurate
+    assert e3 < 2e-5 and e4 < 1e-6 and e4 < e3
+    assert e32 < 2e-5  # FP32 GEMM on the same data, for scale
